@@ -1,0 +1,186 @@
+/*
+ * lidog_b200.h -- C ABI of the B200-native LiDOG hot path (liblidog_b200.so, sm_100a).
+ *
+ * The reference (saltoricristiano/lidog) reaches its hot path only through the
+ * Python package MinkowskiEngine 0.5.4 (reference README.md:29), whose pybind
+ * module `MinkowskiEngineBackend._C` is what these entry points replace.  Each
+ * function names the reference call site (file:line under /root/reference) that
+ * fixes its contract; the ME-internal convention it follows is in SURVEY.md
+ * Appendix C.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it
+ *     says "host"; the caller owns and allocates all memory (outputs included);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = OK, negative = error (lg_last_error_string() explains);
+ *     data-dependent errors (coordinate outside the packed-key range) are
+ *     reported through the device status word documented per function;
+ *   - rows of coordinate matrices are int32 (batch, x, y, z); feature matrices
+ *     are row-major float32.
+ */
+#ifndef LIDOG_B200_H
+#define LIDOG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_ERR_INVALID -1     /* bad argument (shape, alignment, unsupported size) */
+#define LG_ERR_CUDA -2        /* CUDA runtime / driver error */
+#define LG_ERR_RANGE -3       /* coordinate outside the 16-bit-per-axis key range (device status) */
+#define LG_ERR_UNSUPPORTED -4 /* shape not supported by the tensor-core path */
+
+#define LG_TILE_ROWS 128 /* rows per gather tile; n_slots of every plan is a multiple of it */
+
+/* operand formats of the tensor-core kernels (kind::f16 tcgen05.mma, fp32 accumulate) */
+#define LG_FMT_BF16 0
+#define LG_FMT_FP16 1
+
+/* BEV duplicate-pixel policies */
+#define LG_BEV_LAST 0 /* highest row index wins; gradient to every row of the pixel (reference behaviour) */
+#define LG_BEV_MAX 1  /* channel-wise max; gradient to the first row attaining it (north_star scatter-max) */
+
+int lg_version(void);
+const char* lg_last_error_string(void); /* host string, thread-local */
+int lg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ hash / voxelisation */
+
+/* Open-addressing table: 16 bytes per slot {uint64 key, int32 value, pad}. */
+int64_t lg_hash_capacity(int64_t n_keys); /* power of two >= 2*n_keys */
+size_t lg_hash_bytes(int64_t capacity);
+
+/* q = int32(floor(points / size)) in float32 division, per axis; writes (batch, qx, qy, qz).
+ * Replaces the quantisation half of ME.utils.sparse_quantize
+ * (call sites utils/datasets/semantickitti_bev.py:232-238, synth4d_bev.py:274-280,
+ * nuscenes_bev.py:244-250, mix3D.py:67-72).  batch_of_row may be NULL (batch 0). */
+int lg_quantize_points(const float* points_xyz, const int32_t* batch_of_row, int64_t n, float size_x, float size_y,
+                       float size_z, int32_t* coords4_out, void* stream);
+
+size_t lg_coords_unique_workspace(int64_t n);
+
+/* Unique coordinates in first-occurrence order + hash table build.
+ * coords' = floor(coords / stride) * stride on the 3 spatial axes (stride 1 = as is).
+ *   table/capacity : filled with key -> unique row id (usable by lg_kernel_map afterwards)
+ *   out_coords4    : [>= n, 4] unique (strided) coordinates, first-occurrence order
+ *   unique_map     : [>= n] input row of each unique voxel (ascending)
+ *   inverse_map    : [n] unique id of every input row
+ *   labels/colabels: optional; colabel = common label of the voxel or ignore_label
+ *   count_status   : int64[2] = {n_unique, status (0 or LG_ERR_RANGE)}
+ * Replaces: the unique/inverse half of sparse_quantize (same call sites), the
+ * coordinate-manager insert of ME.SparseTensor (utils/pipelines/trainer_lighting_2d.py:151)
+ * and the stride-2 coordinate maps implied by MinkowskiConvolution(stride=2)
+ * (utils/models/minkunet_bev.py:62,69,76,83). */
+int lg_coords_unique(const int32_t* coords4, int64_t n, int32_t stride, void* table, int64_t capacity,
+                     int32_t* out_coords4, int64_t* unique_map, int64_t* inverse_map, const int32_t* labels,
+                     int32_t ignore_label, int32_t* colabels, int64_t* count_status, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ kernel maps */
+
+/* Gather plan consumed by the convolution kernels.  For slot s of tile t = s / LG_TILE_ROWS and
+ * kernel offset k with bit k set in tile_mask[t]:  the operand row is nbr[k * k_stride + s]
+ * (-1 = no neighbour = zero row) and the result row is out_row[s] (NULL = s itself). */
+typedef struct lgConvPlan {
+  const int32_t* nbr;
+  int64_t k_stride; /* n_slots, or 0 when a tile uses one k only (transposed stride-2 plans) */
+  const int32_t* out_row;
+  const uint32_t* tile_mask; /* [n_slots / LG_TILE_ROWS][mask_words] */
+  int32_t kernel_volume;     /* K */
+  int32_t mask_words;        /* ceil(K / 32) */
+  int64_t n_slots;
+  int64_t n_out; /* rows of the result matrix */
+  int64_t n_in;  /* rows of the gathered matrix */
+} lgConvPlan;
+
+/* Neighbour table for out voxel o and offset k (x fastest; odd size centred, even size 0-based;
+ * offsets scaled by offset_scale = input tensor stride):  nbr[k][o] = row of (o + off_k) in table_in.
+ * Replaces ME's kernel-map generation implied by every MinkowskiConvolution
+ * (utils/models/minkunet_bev.py:57-123,410-442).  n_slots = round_up(n_out, LG_TILE_ROWS). */
+int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
+                  int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int64_t n_slots, uint32_t* tile_mask,
+                  void* stream);
+
+size_t lg_scan_workspace(int64_t n_items);
+
+/* ME-format pair lists from a neighbour table: pairs sorted by (k, out);
+ * k_offsets int64[K+1] = start of each offset's list (k_offsets[K] = total). */
+int lg_kernel_map_pairs(const int32_t* nbr, int32_t K, int64_t n_slots, int32_t* in_rows, int32_t* out_rows,
+                        int64_t* k_offsets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stride-2, kernel-2 "up" plan (transposed convolution coarse -> fine, and dgrad of the stride-2
+ * convolution): fine rows grouped by child index k, each group padded to LG_TILE_ROWS.
+ *   parent_of_fine : int64 [n_fine] (inverse_map of the stride-2 lg_coords_unique call)
+ *   gather[n_slots], out_row[n_slots], tile_mask[n_slots/128] are outputs;
+ *   n_slots must be >= round_up(n_fine, 128) + 8 * 128;  slots_used int64[1] receives the used count.
+ * Replaces ME's transposed kernel map (utils/models/minkunet_bev.py:89,96,103,110). */
+int lg_kernel_map_up2(const int32_t* fine_coords4, const int64_t* parent_of_fine, int64_t n_fine,
+                      int32_t fine_stride, int32_t* gather, int32_t* out_row, uint32_t* tile_mask, int64_t n_slots,
+                      int64_t* slots_used, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ sparse convolution */
+
+/* fp32 SIMT gather-GEMM:  Y[out_row[s], :] = sum_k A[nbr[k][s], :] @ Wk,  Wk = W[wk] (Ca x N) or its
+ * transpose when w_transposed (W stored [K][N][Ca]); wk = K-1-k when flip_k.  Used for shapes the
+ * tensor-core path does not take (Cin = 1 stem, Cout = 7 head) and as the on-device fp32 check.
+ * bias (nullable, [N]) is added once per row.  Rows without any pair receive bias / zero. */
+int lg_conv_gemm_simt(const lgConvPlan* plan, const float* A, int32_t Ca, const float* W, int32_t N,
+                      int32_t w_transposed, int32_t flip_k, const float* bias, float* Y, void* stream);
+
+size_t lg_conv_wgrad_workspace(const lgConvPlan* plan, int32_t Ca, int32_t Cb);
+
+/* dW[k] (Cin x Cout) = sum_s X_in[nbr[k][s], :]^T dY_out[out_row[s] (or s), :] over the slots of the
+ * tiles whose mask has bit k.  Deterministic two-pass reduction through `workspace`. */
+int lg_conv_wgrad_simt(const lgConvPlan* plan, const float* X_in, int32_t Cin, const float* dY_out, int32_t Cout,
+                       float* dW, void* workspace, size_t workspace_bytes, void* stream);
+
+/* fp32 -> 16-bit operand rows, value * scale[0] when scale != NULL (device float). */
+int lg_cast_rows(const float* src, void* dst16, int64_t n_elems, int32_t fmt, const float* scale, void* stream);
+/* scale_out float[4]: [0] = power of two bringing absmax(src) into [2^11, 2^12), [1] = 1/[0],
+ * [2] scratch. */
+int lg_absmax_scale(const float* src, int64_t n_elems, float* scale_out, void* stream);
+/* W fp32 [K][Cin][Cout] -> w16 [K][Cin][Cout] and w16t [K][Cout][Cin] (either may be NULL). */
+int lg_prep_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout, void* w16, void* w16t, int32_t fmt,
+                    void* stream);
+
+/* tcgen05 gather-GEMM (forward and dgrad of MinkowskiConvolution / MinkowskiConvolutionTranspose,
+ * utils/models/minkunet_bev.py:57-123):  Y[out_row[s], :] = out_scale * sum_k A16[nbr[k][s], :] @ B16[wk]^T
+ * A16 [n_in][Ck] and B16 [K][N][Ck] are 16-bit (fmt), Ck % 32 == 0, N % 16 == 0, N <= 512.
+ * out_scale: nullable device float (undoes lg_absmax_scale).  bias nullable [N].
+ * gather_mode: 1 = TMA (tile::gather4 rows + tiled weight slabs), 0 = cp.async with zero fill. */
+int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t Ck, const void* B16, int32_t N, int32_t flip_k,
+                    int32_t fmt, const float* out_scale, const float* bias, float* Y, int32_t gather_mode,
+                    void* stream);
+
+size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin, int32_t Cout);
+/* tcgen05 wgrad: dW[k] = out_scale * sum_s X16[nbr[k][s], :]^T dY16[out_row[s], :]  (fp32 [K][Cin][Cout]). */
+int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const void* dY16, int32_t Cout,
+                     int32_t fmt, const float* out_scale, float* dW, int32_t gather_mode, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ BEV projection */
+
+size_t lg_bev_workspace(int64_t n, int32_t batch_size, int32_t H, int32_t W);
+
+/* Fused point-to-BEV projection: pixel scatter + raw (H,W,C)->(C,H,W) re-view + MaxPool2d(pk,ps,pp),
+ * never materialising the dense tensor.  Replaces MinkUNetBaseBEV.sparse2super + filter_bounds
+ * (utils/models/minkunet_bev.py:158-230).  out: float [batch, C, h, w], h = (H + 2pp - pk)/ps + 1.
+ * workspace keeps the pixel map for lg_bev_backward. */
+int lg_bev_forward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size, float bound,
+                   float voxel_size, int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy,
+                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (autograd of index_put_ + max_pool2d at minkunet_bev.py:217-221).
+ * grad_feats [n, C] is fully written. */
+int lg_bev_backward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size,
+                    int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy, const float* grad_out,
+                    float* grad_feats, const void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDOG_B200_H */

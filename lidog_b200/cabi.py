@@ -1,0 +1,97 @@
+"""ctypes binding of liblidog_b200.so (the C ABI declared in include/lidog_b200.h).
+
+PyTorch is used only for device memory and streams: tensors are passed as raw
+`data_ptr()`s, the stream as `torch.cuda.current_stream().cuda_stream`.
+There is NO CPU fallback: if the library is missing or a call fails, a
+RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "liblidog_b200.so")
+
+TILE = 128
+FMT_BF16, FMT_FP16 = 0, 1
+BEV_LAST, BEV_MAX = 0, 1
+ERR_RANGE = -3
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class ConvPlan(C.Structure):
+    _fields_ = [("nbr", _vp), ("k_stride", _i64), ("out_row", _vp), ("tile_mask", _vp), ("kernel_volume", _i32),
+                ("mask_words", _i32), ("n_slots", _i64), ("n_out", _i64), ("n_in", _i64)]
+
+
+_PP = C.POINTER(ConvPlan)
+
+SIGNATURES = {
+    "lg_version": (C.c_int, []),
+    "lg_last_error_string": (C.c_char_p, []),
+    "lg_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "lg_hash_capacity": (_i64, [_i64]),
+    "lg_hash_bytes": (_sz, [_i64]),
+    "lg_quantize_points": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp]),
+    "lg_coords_unique_workspace": (_sz, [_i64]),
+    "lg_coords_unique": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "lg_kernel_map": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "lg_scan_workspace": (_sz, [_i64]),
+    "lg_kernel_map_pairs": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lg_kernel_map_up2": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "lg_conv_gemm_simt": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lg_conv_wgrad_workspace": (_sz, [_PP, _i32, _i32]),
+    "lg_conv_wgrad_simt": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "lg_cast_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "lg_absmax_scale": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "lg_prep_weights": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "lg_conv_gemm_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "lg_conv_wgrad_tc_workspace": (_sz, [_PP, _i32, _i32]),
+    "lg_conv_wgrad_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32]),
+    "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
+                                 _sz, _vp]),
+    "lg_bev_backward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz,
+                                  _vp]),
+}
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is not there."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -m lidog_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise RuntimeError(f"liblidog_b200 {what} failed ({rc}): {lib().lg_last_error_string().decode()}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib().lg_device_info(C.byref(a), C.byref(b), C.byref(c)), "lg_device_info")
+    return a.value, b.value, c.value
+
+
+def make_plan(nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in) -> ConvPlan:
+    return ConvPlan(ptr(nbr), k_stride, ptr(out_row), ptr(tile_mask), K, (K + 31) // 32, n_slots, n_out, n_in)

@@ -1,0 +1,237 @@
+// fp32 SIMT gather-GEMM and wgrad over a gather plan.  These are the exact-fp32 kernels used for the
+// layer shapes the tensor-core path does not take (1-channel stem, 7-class head) and as the on-device
+// fp32 cross-check of the tcgen05 kernels.  Output-stationary: every output row is produced by one
+// CTA, so there are no atomics and the summation order is fixed (k ascending, channel ascending).
+// Reference contract: MinkowskiConvolution forward/backward, utils/models/minkunet_bev.py:57-123.
+#include "common.cuh"
+
+namespace lg {
+
+constexpr int TM = LG_TILE_ROWS;  // 128 slots per CTA
+constexpr int TN = 64;            // output columns per CTA
+constexpr int TK = 16;            // reduction chunk
+
+// Y[out_row[s], n0:n0+64] = sum_k A[nbr[k][s], :] @ Wk[:, n0:n0+64]
+__global__ void __launch_bounds__(256)
+    k_gemm_simt(lgConvPlan plan, const float* __restrict__ A, int Ca, const float* __restrict__ W, int N,
+                int w_transposed, int flip_k, const float* __restrict__ bias, float* __restrict__ Y) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN];
+  __shared__ int s_row[TM];
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int n0 = blockIdx.y * TN;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 8 rows x 4 cols each
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int K = plan.kernel_volume;
+  for (int k = 0; k < K; ++k) {
+    const uint32_t m = plan.tile_mask[tile * plan.mask_words + (k >> 5)];
+    if (!((m >> (k & 31)) & 1u)) continue;
+    const int wk = flip_k ? (K - 1 - k) : k;
+    __syncthreads();
+    if (tid < TM) s_row[tid] = plan.nbr[(int64_t)k * plan.k_stride + tile * TM + tid];
+    for (int c0 = 0; c0 < Ca; c0 += TK) {
+      const int kc = min(TK, Ca - c0);
+      __syncthreads();
+      // A chunk: 128 rows x kc
+      for (int e = tid; e < TM * TK; e += 256) {
+        const int r = e / TK, c = e % TK;
+        const int row = s_row[r];
+        As[c][r] = (row >= 0 && c < kc) ? __ldg(A + (int64_t)row * Ca + c0 + c) : 0.f;
+      }
+      // B chunk: kc x 64
+      for (int e = tid; e < TK * TN; e += 256) {
+        const int c = e / TN, n = e % TN;
+        float v = 0.f;
+        if (c < kc && n0 + n < N) {
+          v = w_transposed ? __ldg(W + ((int64_t)wk * N + (n0 + n)) * Ca + c0 + c)
+                           : __ldg(W + ((int64_t)wk * Ca + (c0 + c)) * N + n0 + n);
+        }
+        Bs[c][n] = v;
+      }
+      __syncthreads();
+      for (int c = 0; c < kc; ++c) {
+        float a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = As[c][ty * 8 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[c][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t s = tile * TM + ty * 8 + i;
+    int64_t row = plan.out_row ? (int64_t)plan.out_row[s] : s;
+    if (row < 0 || row >= plan.n_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) Y[row * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// Partial dW for one (k, slot chunk, 64x64 tile of Cin x Cout):
+//   P[chunk][k][ci][co] = sum_{s in chunk} X[nbr[k][s], ci] * dY[out_row[s], co]
+constexpr int WG_T = 64;
+constexpr int WG_S = 16;  // slots per smem step
+
+__global__ void __launch_bounds__(256)
+    k_wgrad_simt(lgConvPlan plan, const float* __restrict__ X, int Cin, const float* __restrict__ dY, int Cout,
+                 int tiles_per_chunk, float* __restrict__ partial) {
+  __shared__ float Xs[WG_S][WG_T + 1];
+  __shared__ float Ds[WG_S][WG_T + 1];
+  __shared__ int s_in[WG_S], s_out[WG_S];
+  const int tid = threadIdx.x;
+  const int k = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int tiles_b = (Cout + WG_T - 1) / WG_T;
+  const int a0 = (blockIdx.z / tiles_b) * WG_T, b0 = (blockIdx.z % tiles_b) * WG_T;
+  const int ty = tid >> 4, tx = tid & 15;  // 4 x 4 outputs per thread
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int64_t n_tiles = plan.n_slots / TM;
+  const int64_t t_begin = (int64_t)chunk * tiles_per_chunk;
+  const int64_t t_end = (n_tiles < t_begin + tiles_per_chunk) ? n_tiles : t_begin + tiles_per_chunk;
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const uint32_t m = plan.tile_mask[tile * plan.mask_words + (k >> 5)];
+    if (!((m >> (k & 31)) & 1u)) continue;
+    for (int s0 = 0; s0 < TM; s0 += WG_S) {
+      __syncthreads();
+      if (tid < WG_S) {
+        const int64_t s = tile * TM + s0 + tid;
+        int in = plan.nbr[(int64_t)k * plan.k_stride + s];
+        int64_t out = plan.out_row ? (int64_t)plan.out_row[s] : s;
+        if (out < 0 || out >= plan.n_out) in = -1;
+        s_in[tid] = in;
+        s_out[tid] = (int)out;
+      }
+      __syncthreads();
+      for (int e = tid; e < WG_S * WG_T; e += 256) {
+        const int r = e / WG_T, c = e % WG_T;
+        const int in = s_in[r];
+        Xs[r][c] = (in >= 0 && a0 + c < Cin) ? __ldg(X + (int64_t)in * Cin + a0 + c) : 0.f;
+        Ds[r][c] = (in >= 0 && b0 + c < Cout) ? __ldg(dY + (int64_t)s_out[r] * Cout + b0 + c) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < WG_S; ++r) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Xs[r][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Ds[r][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+  float* P = partial + ((int64_t)chunk * plan.kernel_volume + k) * Cin * Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + ty * 4 + i, b = b0 + tx * 4 + j;
+      if (a < Cin && b < Cout) P[(int64_t)a * Cout + b] = acc[i][j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_reduce_partials(const float* __restrict__ partial, int n_chunks, int64_t n_elems, float scale_mode,
+                      const float* __restrict__ out_scale, float* __restrict__ dW) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elems) return;
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += partial[(int64_t)c * n_elems + i];  // fixed order
+  dW[i] = out_scale ? s * out_scale[0] : s;
+}
+
+int wgrad_chunks(const lgConvPlan* plan, int* tiles_per_chunk) {
+  const int64_t n_tiles = plan->n_slots / TM;
+  int64_t want = 592 / (plan->kernel_volume > 0 ? plan->kernel_volume : 1);
+  if (want < 1) want = 1;
+  int chunks = (int)(n_tiles < want ? n_tiles : want);
+  if (chunks < 1) chunks = 1;
+  *tiles_per_chunk = (int)ceil_div(n_tiles, chunks);
+  chunks = (int)ceil_div(n_tiles, *tiles_per_chunk);
+  return chunks < 1 ? 1 : chunks;
+}
+
+int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
+                           cudaStream_t stream) {
+  k_reduce_partials<<<(unsigned)ceil_div(n_elems, 256), 256, 0, stream>>>(partial, n_chunks, n_elems, 0.f, out_scale,
+                                                                          dW);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+}  // namespace lg
+
+using namespace lg;
+
+static int check_plan(const lgConvPlan* p, const char* who) {
+  LG_CHECK_ARG(p != nullptr, "%s: null plan", who);
+  LG_CHECK_ARG(p->n_slots >= 0 && p->n_slots % LG_TILE_ROWS == 0, "%s: n_slots must be a multiple of 128", who);
+  LG_CHECK_ARG(p->kernel_volume >= 1 && p->kernel_volume <= 128 && p->mask_words == (p->kernel_volume + 31) / 32,
+               "%s: bad kernel_volume/mask_words", who);
+  LG_CHECK_ARG(p->k_stride == 0 || p->k_stride == p->n_slots, "%s: k_stride must be 0 or n_slots", who);
+  if (p->n_slots > 0) LG_CHECK_ARG(p->nbr && p->tile_mask, "%s: null plan arrays", who);
+  return LG_OK;
+}
+
+extern "C" int lg_conv_gemm_simt(const lgConvPlan* plan, const float* A, int32_t Ca, const float* W, int32_t N,
+                                 int32_t w_transposed, int32_t flip_k, const float* bias, float* Y, void* stream) {
+  int rc = check_plan(plan, "lg_conv_gemm_simt");
+  if (rc) return rc;
+  LG_CHECK_ARG(Ca >= 1 && N >= 1, "lg_conv_gemm_simt: bad channel counts");
+  if (plan->n_slots == 0) return LG_OK;
+  LG_CHECK_ARG(A && W && Y, "lg_conv_gemm_simt: null pointer");
+  dim3 grid((unsigned)(plan->n_slots / TM), (unsigned)ceil_div(N, TN));
+  k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(*plan, A, Ca, W, N, w_transposed, flip_k, bias, Y);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+extern "C" size_t lg_conv_wgrad_workspace(const lgConvPlan* plan, int32_t Ca, int32_t Cb) {
+  if (!plan) return 0;
+  int tpc;
+  int chunks = wgrad_chunks(plan, &tpc);
+  return (size_t)chunks * plan->kernel_volume * Ca * Cb * sizeof(float) + 256;
+}
+
+extern "C" int lg_conv_wgrad_simt(const lgConvPlan* plan, const float* X_in, int32_t Cin, const float* dY_out,
+                                  int32_t Cout, float* dW, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_plan(plan, "lg_conv_wgrad_simt");
+  if (rc) return rc;
+  LG_CHECK_ARG(Cin >= 1 && Cout >= 1 && dW, "lg_conv_wgrad_simt: bad arguments");
+  const int64_t n_elems = (int64_t)plan->kernel_volume * Cin * Cout;
+  if (plan->n_slots == 0) {
+    LG_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * n_elems, stream));
+    return LG_OK;
+  }
+  LG_CHECK_ARG(workspace && workspace_bytes >= lg_conv_wgrad_workspace(plan, Cin, Cout),
+               "lg_conv_wgrad_simt: workspace too small");
+  int tpc;
+  const int chunks = wgrad_chunks(plan, &tpc);
+  dim3 grid((unsigned)plan->kernel_volume, (unsigned)chunks,
+            (unsigned)(ceil_div(Cin, WG_T) * ceil_div(Cout, WG_T)));
+  k_wgrad_simt<<<grid, 256, 0, stream>>>(*plan, X_in, Cin, dY_out, Cout, tpc, (float*)workspace);
+  LG_LAUNCH_OK();
+  return launch_reduce_partials((const float*)workspace, chunks, n_elems, nullptr, dW, stream);
+}

@@ -1,0 +1,195 @@
+// Kernel-map generation: neighbour tables by hash probes, per-tile offset masks, ME-format pair
+// lists, and the k-sorted stride-2 "up" plan.  Reference contract: the kernel maps implied by every
+// MinkowskiConvolution / MinkowskiConvolutionTranspose in utils/models/minkunet_bev.py:57-123,410-442
+// (conventions: SURVEY.md Appendix C.7).  A warp owns 32 consecutive output voxels and walks the
+// kernel offsets together, so nbr[k][o..o+31] is written coalesced and the tile mask falls out of a
+// ballot; the table (16 B slots, load factor <= 0.5) stays L2-resident.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace lg {
+
+constexpr int kMaxMaskWords = 4;  // K <= 128 (5^3 = 125)
+
+__global__ void __launch_bounds__(LG_TILE_ROWS)
+    k_neighbors(const HashSlot* __restrict__ table, unsigned long long mask, const int4* __restrict__ out_coords,
+                int64_t n_out, int ksize, int scale, int K, int mask_words, int32_t* __restrict__ nbr,
+                int64_t n_slots, uint32_t* __restrict__ tile_mask) {
+  __shared__ uint32_t s_mask[kMaxMaskWords];
+  if (threadIdx.x < kMaxMaskWords) s_mask[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t o = (int64_t)blockIdx.x * LG_TILE_ROWS + threadIdx.x;
+  const bool valid = o < n_out;
+  int4 c = valid ? out_coords[o] : make_int4(0, 0, 0, 0);
+  const int base = (ksize & 1) ? -(ksize / 2) : 0;
+  uint32_t wmask[kMaxMaskWords] = {0, 0, 0, 0};
+  int k = 0;
+  for (int iz = 0; iz < ksize; ++iz)
+    for (int iy = 0; iy < ksize; ++iy)
+      for (int ix = 0; ix < ksize; ++ix, ++k) {
+        int r = -1;
+        if (valid) {
+          int x = c.y + (base + ix) * scale, y = c.z + (base + iy) * scale, z = c.w + (base + iz) * scale;
+          if (coord_in_range(c.x, x, y, z)) r = hash_lookup(table, mask, pack_key(c.x, x, y, z));
+        }
+        nbr[(int64_t)k * n_slots + o] = r;
+        if (__ballot_sync(0xffffffffu, r >= 0)) wmask[k >> 5] |= 1u << (k & 31);
+      }
+  if ((threadIdx.x & 31) == 0) {
+    for (int w = 0; w < mask_words; ++w)
+      if (wmask[w]) atomicOr(&s_mask[w], wmask[w]);
+  }
+  __syncthreads();
+  if (threadIdx.x < mask_words) tile_mask[(int64_t)blockIdx.x * mask_words + threadIdx.x] = s_mask[threadIdx.x];
+}
+
+// ---- ME-format pair lists: flatten [K][n_slots], keep entries >= 0 (order = (k, out) ascending)
+struct PairFlag {
+  const int32_t* nbr;
+  __device__ bool operator()(int64_t i) const { return nbr[i] >= 0; }
+};
+struct PairSink {
+  const int32_t* nbr;
+  int64_t n_slots;
+  int32_t* in_rows;
+  int32_t* out_rows;
+  int64_t* k_offsets;
+  __device__ void operator()(int64_t i, int prefix, bool f) const {
+    const int64_t k = i / n_slots, o = i - k * n_slots;
+    if (o == 0) k_offsets[k] = prefix;
+    if (f) {
+      in_rows[prefix] = nbr[i];
+      out_rows[prefix] = (int32_t)o;
+    }
+  }
+};
+
+// ---- stride-2 "up" plan: fine rows grouped by child index
+__device__ __forceinline__ int child_index(int4 c, int ts) {
+  return (floor_div(c.y, ts) & 1) | ((floor_div(c.z, ts) & 1) << 1) | ((floor_div(c.w, ts) & 1) << 2);
+}
+struct ChildFlag {
+  const int4* coords;
+  int64_t n;
+  int ts;
+  __device__ bool operator()(int64_t i) const {
+    const int64_t k = i / n, r = i - k * n;
+    return child_index(coords[r], ts) == (int)k;
+  }
+};
+struct ChildSink {  // pass 1: only the per-k starts
+  int64_t n;
+  int* k_start;  // [9]
+  __device__ void operator()(int64_t i, int prefix, bool f) const {
+    const int64_t k = i / n;
+    if (i - k * n == 0) k_start[k] = prefix;
+  }
+};
+struct ChildFill {
+  const int64_t* parent;
+  int64_t n;
+  const int* k_start;      // [9] (k_start[8] = n)
+  const int* k_slot_base;  // [9] padded segment starts
+  int32_t* gather;
+  int32_t* out_row;
+  __device__ void operator()(int64_t i, int prefix, bool f) const {
+    if (!f) return;
+    const int64_t k = i / n, r = i - k * n;
+    const int slot = k_slot_base[k] + (prefix - k_start[k]);
+    gather[slot] = (int32_t)parent[r];
+    out_row[slot] = (int32_t)r;
+  }
+};
+
+__global__ void k_up2_layout(const int* k_start, int64_t n, int* k_slot_base, uint32_t* tile_mask, int64_t n_tiles_cap,
+                             int64_t* slots_used) {
+  // single thread: 8 segments
+  int base = 0;
+  for (int k = 0; k < 8; ++k) {
+    int cnt = ((k == 7) ? (int)n : k_start[k + 1]) - k_start[k];
+    k_slot_base[k] = base;
+    int tiles = (cnt + LG_TILE_ROWS - 1) / LG_TILE_ROWS;
+    for (int t = 0; t < tiles; ++t) {
+      int64_t tile = base / LG_TILE_ROWS + t;
+      if (tile < n_tiles_cap) tile_mask[tile] = 1u << k;
+    }
+    base += tiles * LG_TILE_ROWS;
+  }
+  k_slot_base[8] = base;
+  *slots_used = base;
+}
+
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace lg
+
+using namespace lg;
+
+extern "C" int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
+                             int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int64_t n_slots,
+                             uint32_t* tile_mask, void* stream) {
+  LG_CHECK_ARG(kernel_size >= 1 && kernel_size <= 5, "lg_kernel_map: kernel_size %d not in [1,5]", kernel_size);
+  LG_CHECK_ARG(n_out >= 0 && n_slots == round_up(n_out, LG_TILE_ROWS), "lg_kernel_map: n_slots must be round_up(n_out,128)");
+  LG_CHECK_ARG(capacity_in >= 1024 && (capacity_in & (capacity_in - 1)) == 0, "lg_kernel_map: bad capacity");
+  if (n_out == 0) return LG_OK;
+  LG_CHECK_ARG(table_in && out_coords4 && nbr && tile_mask, "lg_kernel_map: null pointer");
+  const int K = kernel_size * kernel_size * kernel_size;
+  const int words = (K + 31) / 32;
+  k_neighbors<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, (cudaStream_t)stream>>>(
+      (const HashSlot*)table_in, (unsigned long long)(capacity_in - 1), (const int4*)out_coords4, n_out, kernel_size,
+      offset_scale, K, words, nbr, n_slots, tile_mask);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+extern "C" size_t lg_scan_workspace(int64_t n_items) { return scan_workspace_bytes(n_items > 0 ? n_items : 1) + 1024; }
+
+extern "C" int lg_kernel_map_pairs(const int32_t* nbr, int32_t K, int64_t n_slots, int32_t* in_rows, int32_t* out_rows,
+                                   int64_t* k_offsets, void* workspace, size_t workspace_bytes, void* stream) {
+  LG_CHECK_ARG(K >= 1 && n_slots >= 0 && k_offsets, "lg_kernel_map_pairs: bad arguments");
+  const int64_t n = (int64_t)K * n_slots;
+  LG_CHECK_ARG(workspace_bytes >= lg_scan_workspace(n), "lg_kernel_map_pairs: workspace too small");
+  if (n == 0) {
+    LG_CUDA_OK(cudaMemsetAsync(k_offsets, 0, sizeof(int64_t) * (K + 1), (cudaStream_t)stream));
+    return LG_OK;
+  }
+  PairFlag flag{nbr};
+  PairSink sink{nbr, n_slots, in_rows, out_rows, k_offsets};
+  return device_scan(flag, sink, n, k_offsets + K, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int lg_kernel_map_up2(const int32_t* fine_coords4, const int64_t* parent_of_fine, int64_t n_fine,
+                                 int32_t fine_stride, int32_t* gather, int32_t* out_row, uint32_t* tile_mask,
+                                 int64_t n_slots, int64_t* slots_used, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LG_CHECK_ARG(n_fine >= 0 && fine_stride >= 1, "lg_kernel_map_up2: bad arguments");
+  LG_CHECK_ARG(n_slots % LG_TILE_ROWS == 0 && n_slots >= round_up(n_fine, LG_TILE_ROWS) + 8 * LG_TILE_ROWS,
+               "lg_kernel_map_up2: n_slots too small");
+  const int64_t n = 8 * n_fine;
+  const size_t need = lg_scan_workspace(n) + 256;
+  LG_CHECK_ARG(workspace_bytes >= need, "lg_kernel_map_up2: workspace too small");
+  LG_CHECK_ARG(gather && out_row && tile_mask && slots_used && workspace, "lg_kernel_map_up2: null pointer");
+  int* k_start = (int*)workspace;  // [9] + k_slot_base [9]
+  int* k_slot_base = k_start + 16;
+  void* scan_ws = (char*)workspace + 256;
+  LG_CUDA_OK(cudaMemsetAsync(tile_mask, 0, sizeof(uint32_t) * (size_t)(n_slots / LG_TILE_ROWS), stream));
+  k_fill_i32<<<(unsigned)ceil_div(n_slots, 256), 256, 0, stream>>>(gather, n_slots, -1);
+  k_fill_i32<<<(unsigned)ceil_div(n_slots, 256), 256, 0, stream>>>(out_row, n_slots, -1);
+  LG_LAUNCH_OK();
+  if (n_fine == 0) {
+    LG_CUDA_OK(cudaMemsetAsync(slots_used, 0, sizeof(int64_t), stream));
+    return LG_OK;
+  }
+  ChildFlag flag{(const int4*)fine_coords4, n_fine, fine_stride};
+  ChildSink s1{n_fine, k_start};
+  int rc = device_scan(flag, s1, n, nullptr, scan_ws, stream);
+  if (rc != LG_OK) return rc;
+  k_up2_layout<<<1, 1, 0, stream>>>(k_start, n_fine, k_slot_base, tile_mask, n_slots / LG_TILE_ROWS, slots_used);
+  LG_LAUNCH_OK();
+  ChildFill s2{parent_of_fine, n_fine, k_start, k_slot_base, gather, out_row};
+  return device_scan(flag, s2, n, nullptr, scan_ws, stream);
+}

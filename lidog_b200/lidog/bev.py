@@ -1,0 +1,82 @@
+"""Fused point-to-BEV projection operator (CUDA, csrc/bev.cu) with autograd.
+
+Replaces `MinkUNetBaseBEV.sparse2super` + `filter_bounds` of the reference
+(utils/models/minkunet_bev.py:158-230) without the D2H copy of the coordinates,
+the per-sample Python loop and the dense 2000 x 2000 x C tensor.
+`patch_reference_model` swaps it into an instance of the reference's own class.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+
+from .. import cabi
+
+POLICIES = {"last": cabi.BEV_LAST, "max": cabi.BEV_MAX}
+
+
+def image_size(bound: float, voxel_size: float) -> int:
+    # max_height / max_width exactly as minkunet_bev.py:184-185 computes them
+    return int(torch.tensor((bound - (-bound)) / voxel_size).int())
+
+
+class BevProjectFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, coords, batch_size, bound, voxel_size, pool, policy):
+        L = cabi.lib()
+        feats_c = feats.detach().contiguous()
+        coords = coords.contiguous()
+        n, C = feats_c.shape
+        H = W = image_size(bound, voxel_size)
+        pk, ps, pp = pool
+        h = (H + 2 * pp - pk) // ps + 1
+        w = (W + 2 * pp - pk) // ps + 1
+        out = torch.empty((batch_size, C, h, w), dtype=torch.float32, device=feats.device)
+        ws_bytes = L.lg_bev_workspace(n, batch_size, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+        cabi.check(L.lg_bev_forward(cabi.ptr(coords), cabi.ptr(feats_c), n, C, batch_size, float(bound),
+                                    float(voxel_size), H, W, pk, ps, pp, policy, cabi.ptr(out), cabi.ptr(ws), ws_bytes,
+                                    cabi.stream()), "lg_bev_forward")
+        ctx.save_for_backward(feats_c, coords, ws)
+        ctx.args = (n, C, batch_size, H, W, pk, ps, pp, policy, ws_bytes)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feats, coords, ws = ctx.saved_tensors
+        n, C, batch_size, H, W, pk, ps, pp, policy, ws_bytes = ctx.args
+        grad_out = grad_out.contiguous()
+        grad_feats = torch.empty((n, C), dtype=torch.float32, device=feats.device)
+        cabi.check(cabi.lib().lg_bev_backward(cabi.ptr(coords), cabi.ptr(feats), n, C, batch_size, H, W, pk, ps, pp,
+                                              policy, cabi.ptr(grad_out), cabi.ptr(grad_feats), cabi.ptr(ws), ws_bytes,
+                                              cabi.stream()), "lg_bev_backward")
+        return grad_feats, None, None, None, None, None, None
+
+
+def bev_project(coords, feats, batch_size, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last"):
+    return BevProjectFunction.apply(feats, coords, int(batch_size), float(bound), float(voxel_size), tuple(pool),
+                                    POLICIES[policy])
+
+
+def sparse2super(x, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last", batch_size=None):
+    """x: SparseTensor (any tensor stride; coordinates in stride-1 voxel units) -> [B, C, h, w]."""
+    cm = x.coordinate_manager
+    if batch_size is None:
+        batch_size = getattr(cm, "batch_size", None)
+    if batch_size is None:  # reference: batch_bottle_idx.max()+1 (minkunet_bev.py:193); one host sync, cached
+        batch_size = int(x.C[:, 0].max().item()) + 1
+        cm.batch_size = batch_size
+    return bev_project(x.C, x.F, batch_size, bound, voxel_size, pool, policy)
+
+
+def patch_reference_model(model, policy="last"):
+    """Route an instance of the reference's MinkUNetBaseBEV (unchanged class) to the fused operator."""
+
+    def _s2s(self, x, input_voxel_size=0.05, scaling_factor=1.0):
+        stride = 3 if scaling_factor == 1.0 else int(3 / scaling_factor)
+        return sparse2super(x, bound=self.mapping_bound_2d, voxel_size=input_voxel_size, pool=(5, stride, 1),
+                            policy=policy)
+
+    model.sparse2super = types.MethodType(_s2s, model)
+    return model

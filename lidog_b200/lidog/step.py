@@ -1,0 +1,88 @@
+"""One LiDOG training step on the GPU hot path.
+
+Mirror of `PLTTrainer2D.training_step` + `configure_optimizers`
+(utils/pipelines/trainer_lighting_2d.py:141-293, 349-360) minus logging/metrics:
+voxelise -> ME.SparseTensor -> MinkUNet34BEV(is_train=True) -> SoftDICE (3D) + DICE (BEV)
+-> backward -> Adam(lr 1e-3, weight_decay 1e-4).  Reference quirks kept on purpose:
+the (B,C,h,w) BEV logits are re-viewed as (-1, C) without a permute (`:181`), the 3D loss
+uses the first point's label per voxel and the BEV image the agree-or-ignore colabel
+(semantickitti_bev.py:242,249).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import losses
+from .synth import SHAPES
+
+
+def bev_label_image(coords4: torch.Tensor, colabels: torch.Tensor, batch_size: int, bound: float, img: int,
+                    voxel_size: float = 0.05) -> torch.Tensor:
+    """Device version of PC2ImgConverter.getBEVImageNew (semantickitti_bev.py:433-464) for a whole
+    batch: int64 [B, img, img], -1 = ignore.  Duplicate pixels: highest row wins (deterministic)."""
+    dev = coords4.device
+    pts = coords4[:, 1:].to(torch.float32) * voxel_size
+    grid = (bound - (-bound)) / img
+    valid = (colabels != -1) & (-bound < pts[:, 0]) & (pts[:, 0] < bound) & (-bound < pts[:, 1]) & \
+            (pts[:, 1] < bound) & (-10 < pts[:, 2]) & (pts[:, 2] < 8)
+    px = torch.floor((pts[:, 0] - (-bound)) / grid).long()
+    py = torch.floor(img - (pts[:, 1] - (-bound)) / grid).long() - 1
+    py = torch.where(py < 0, py + img, py)
+    pix = coords4[:, 0].long() * (img * img) + py.clamp(0, img - 1) * img + px.clamp(0, img - 1)
+    rows = torch.arange(coords4.shape[0], device=dev)
+    rows = torch.where(valid, rows, torch.full_like(rows, -1))
+    win = torch.full((batch_size * img * img,), -1, dtype=torch.long, device=dev)
+    win.scatter_reduce_(0, pix, rows, reduce="amax", include_self=True)
+    lab = torch.where(win >= 0, colabels.long()[win.clamp_min(0)], torch.full_like(win, -1))
+    return lab.view(batch_size, img, img)
+
+
+class LidogTrainer:
+    """Owns model + Adam; `training_step` takes raw device point clouds."""
+
+    def __init__(self, model, num_classes=7, voxel_size=0.05, ignore_label=-1, lr=1e-3, weight_decay=1e-4,
+                 source_weights=(0.5, 0.5), shape="kitti", ME=None):
+        if ME is None:
+            from lidog_b200 import me as ME
+        self.ME, self.model = ME, model
+        self.num_classes, self.voxel_size, self.ignore_label = num_classes, voxel_size, ignore_label
+        self.source_weights = source_weights
+        self.bound, self.bev_img = SHAPES[shape]["bound"], SHAPES[shape]["bev_img"]
+        params = model.parameters()
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
+
+    def voxelize(self, points_list, labels_list):
+        """GPU sparse_quantize of the whole batch (one hash build) + the dataset-side label products."""
+        q = self.ME.utils.sparse_quantize_batch(points_list, labels_list, self.voxel_size, self.ignore_label)
+        labels = torch.cat(labels_list, 0)
+        sem_labels = labels[q["unique_map"]].long()  # first point's label per voxel
+        bev_labels = bev_label_image(q["coords"], q["colabels"], len(points_list), self.bound, self.bev_img,
+                                     self.voxel_size)
+        feats = torch.ones((q["coords"].shape[0], 1), dtype=torch.float32, device=labels.device)
+        cm = None
+        if hasattr(self.ME, "CoordinateManager") and hasattr(self.ME.CoordinateManager, "from_quantized"):
+            cm = self.ME.CoordinateManager.from_quantized(q)  # share the voxelisation hash with the network
+        return q["coords"], feats, sem_labels, bev_labels, cm
+
+    def forward_loss(self, coords, feats, sem_labels, bev_labels, batch_size=None, coordinate_manager=None):
+        if coordinate_manager is not None:
+            stensor = self.ME.SparseTensor(features=feats, coordinate_manager=coordinate_manager)
+        else:
+            stensor = self.ME.SparseTensor(coordinates=coords, features=feats)
+        if batch_size is not None:
+            stensor.coordinate_manager.batch_size = batch_size
+        out, bev_preds = self.model(stensor, is_train=True)
+        loss_bev = 0.0
+        for key, pred in bev_preds.items():
+            loss_bev = loss_bev + losses.dice_loss(pred.reshape(-1, self.num_classes), bev_labels.reshape(-1),
+                                                   self.ignore_label) / len(bev_preds)
+        loss_3d = losses.soft_dice_loss(out.F, sem_labels, self.ignore_label, is_kitti=self.num_classes == 19)
+        return self.source_weights[0] * loss_3d + self.source_weights[1] * loss_bev, loss_3d, loss_bev
+
+    def training_step(self, points_list, labels_list):
+        coords, feats, sem_labels, bev_labels, cm = self.voxelize(points_list, labels_list)
+        self.optimizer.zero_grad(set_to_none=True)
+        total, l3, l2 = self.forward_loss(coords, feats, sem_labels, bev_labels, len(points_list), cm)
+        total.backward()
+        self.optimizer.step()
+        return total.detach()

@@ -1,0 +1,180 @@
+"""CoordinateManager: the shared hashed voxel index of one batch.
+
+Host-side mirror of MinkowskiEngine's coordinate manager as LiDOG exercises it
+(ME.SparseTensor at utils/pipelines/trainer_lighting_2d.py:151; stride-2 maps and
+kernel maps implied by the layers of utils/models/minkunet_bev.py:57-123).  It
+owns, per tensor stride, the unique coordinate list and its GPU hash table, and
+caches one gather plan per (stride_in, stride_out, kernel, kind).  All
+arithmetic happens in liblidog_b200 (csrc/coords.cu, csrc/kmap.cu).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import cabi
+
+
+def _check_count(count_status: torch.Tensor, what: str) -> int:
+    n, status = count_status.tolist()  # one host sync per coordinate level
+    if status != 0:
+        raise RuntimeError(f"{what}: coordinate outside the packed-key range "
+                           f"(|x|,|y|,|z| < 32768, 0 <= batch < 32768); status {status}")
+    return int(n)
+
+
+def coords_unique(coords: torch.Tensor, stride: int = 1, labels: torch.Tensor | None = None, ignore_label: int = -100):
+    """Wrapper of lg_coords_unique -> dict(coords, unique_map, inverse_map, colabels, table, capacity, n)."""
+    assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 4
+    coords = coords.contiguous()
+    L = cabi.lib()
+    n = coords.shape[0]
+    dev = coords.device
+    cap = L.lg_hash_capacity(n)
+    table = torch.empty(L.lg_hash_bytes(cap), dtype=torch.uint8, device=dev)
+    out_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    unique_map = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    inverse_map = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    colabels = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if labels is not None else None
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int32).contiguous()
+    count = torch.empty(2, dtype=torch.int64, device=dev)
+    ws_bytes = L.lg_coords_unique_workspace(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cabi.check(L.lg_coords_unique(cabi.ptr(coords), n, stride, cabi.ptr(table), cap, cabi.ptr(out_coords),
+                                  cabi.ptr(unique_map), cabi.ptr(inverse_map), cabi.ptr(labels), ignore_label,
+                                  cabi.ptr(colabels), cabi.ptr(count), cabi.ptr(ws), ws_bytes, cabi.stream()),
+               "lg_coords_unique")
+    nu = _check_count(count, "lg_coords_unique")
+    return dict(coords=out_coords[:nu], unique_map=unique_map[:nu], inverse_map=inverse_map[:n],
+                colabels=None if colabels is None else colabels[:nu], table=table, capacity=cap, n=nu)
+
+
+class Level:
+    """Coordinates of one tensor stride + their hash table."""
+
+    def __init__(self, coords, table, capacity, parent_of_finer=None):
+        self.coords, self.table, self.capacity = coords, table, capacity
+        self.n = coords.shape[0]
+        self.parent_of_finer = parent_of_finer  # int64 [n_finer]: row here of every row of the finer level
+
+
+class GatherPlan:
+    """Device arrays of one lgConvPlan (kept alive here) + the ctypes struct."""
+
+    def __init__(self, nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in):
+        self.nbr, self.out_row, self.tile_mask = nbr, out_row, tile_mask
+        self.K, self.n_slots, self.n_out, self.n_in, self.k_stride = K, n_slots, n_out, n_in, k_stride
+        self.c = cabi.make_plan(nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in)
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class CoordinateManager:
+    def __init__(self, coordinates: torch.Tensor):
+        res = coords_unique(coordinates, 1)
+        self.device = coordinates.device
+        self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}
+        self.input_unique_map = res["unique_map"]
+        self.input_inverse_map = res["inverse_map"]
+        self.had_duplicates = res["n"] != coordinates.shape[0]
+        self.plans = {}
+
+    @classmethod
+    def from_quantized(cls, res: dict):
+        """Adopt the table built by sparse_quantize(_batch): voxelisation and the network share ONE
+        hashed voxel index (no second hash build for ME.SparseTensor)."""
+        self = cls.__new__(cls)
+        self.device = res["coords"].device
+        self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}
+        self.input_unique_map, self.input_inverse_map = res["unique_map"], res["inverse_map"]
+        self.had_duplicates = False
+        self.plans = {}
+        return self
+
+    # ------------------------------------------------------------------ coordinate levels
+    def level(self, ts: int) -> Level:
+        if ts not in self.levels:
+            if ts < 2 or ts % 2:
+                raise ValueError(f"tensor stride {ts} cannot be derived by stride-2 downsampling")
+            fine = self.level(ts // 2)
+            res = coords_unique(fine.coords, ts)
+            self.levels[ts] = Level(res["coords"], res["table"], res["capacity"], parent_of_finer=res["inverse_map"])
+        return self.levels[ts]
+
+    def get_coords(self, ts: int) -> torch.Tensor:
+        return self.level(ts).coords
+
+    # ------------------------------------------------------------------ gather plans
+    def plan(self, kind: str, ts_in: int, ts_out: int, ksize: int) -> GatherPlan:
+        key = (kind, ts_in, ts_out, ksize)
+        if key not in self.plans:
+            self.plans[key] = getattr(self, "_plan_" + kind)(ts_in, ts_out, ksize)
+        return self.plans[key]
+
+    def _neighbor_plan(self, lvl_in: Level, lvl_out: Level, ksize: int, scale: int) -> GatherPlan:
+        L = cabi.lib()
+        K = ksize ** 3
+        n_out = lvl_out.n
+        n_slots = _round_up(n_out, cabi.TILE)
+        nbr = torch.empty((K, max(n_slots, 1)), dtype=torch.int32, device=self.device)
+        mask = torch.empty((max(n_slots // cabi.TILE, 1), (K + 31) // 32), dtype=torch.int32, device=self.device)
+        cabi.check(L.lg_kernel_map(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out, ksize,
+                                   scale, cabi.ptr(nbr), n_slots, cabi.ptr(mask), cabi.stream()), "lg_kernel_map")
+        return GatherPlan(nbr, n_slots, None, mask, K, n_slots, n_out, lvl_in.n)
+
+    def _plan_same(self, ts_in, ts_out, ksize):
+        assert ts_in == ts_out and ksize % 2 == 1
+        lvl = self.level(ts_in)
+        return self._neighbor_plan(lvl, lvl, ksize, ts_in)
+
+    def _plan_down(self, ts_in, ts_out, ksize):
+        assert ts_out == 2 * ts_in and ksize == 2
+        return self._neighbor_plan(self.level(ts_in), self.level(ts_out), 2, ts_in)
+
+    def _plan_up(self, ts_in, ts_out, ksize):
+        """coarse (ts_in) -> fine (ts_out): fine rows grouped by child index, one k per tile."""
+        assert ts_in == 2 * ts_out and ksize == 2
+        L = cabi.lib()
+        fine, coarse = self.level(ts_out), self.level(ts_in)
+        n_fine = fine.n
+        n_slots = _round_up(n_fine, cabi.TILE) + 8 * cabi.TILE
+        gather = torch.empty(n_slots, dtype=torch.int32, device=self.device)
+        out_row = torch.empty(n_slots, dtype=torch.int32, device=self.device)
+        mask = torch.empty((n_slots // cabi.TILE, 1), dtype=torch.int32, device=self.device)
+        used = torch.empty(1, dtype=torch.int64, device=self.device)
+        ws_bytes = L.lg_scan_workspace(8 * n_fine) + 256
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        cabi.check(L.lg_kernel_map_up2(cabi.ptr(fine.coords), cabi.ptr(coarse.parent_of_finer), n_fine, ts_out,
+                                       cabi.ptr(gather), cabi.ptr(out_row), cabi.ptr(mask), n_slots, cabi.ptr(used),
+                                       cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_kernel_map_up2")
+        return GatherPlan(gather, 0, out_row, mask, 8, n_slots, n_fine, coarse.n)
+
+    def _plan_identity(self, ts_in, ts_out, ksize):
+        assert ts_in == ts_out and ksize == 1
+        n = self.level(ts_in).n
+        n_slots = _round_up(n, cabi.TILE)
+        nbr = torch.arange(n_slots, dtype=torch.int32, device=self.device)
+        nbr[n:] = -1
+        mask = torch.ones((max(n_slots // cabi.TILE, 1), 1), dtype=torch.int32, device=self.device)
+        return GatherPlan(nbr, n_slots, None, mask, 1, n_slots, n, n)
+
+    # ------------------------------------------------------------------ ME-format kernel maps (tests / interop)
+    def kernel_map_pairs(self, plan: GatherPlan):
+        """(in_rows, out_rows, k_offsets) sorted by (k, out) -- MinkowskiEngine's kernel-map format."""
+        if plan.k_stride == 0:
+            raise ValueError("pair lists are defined for neighbour-table plans only")
+        L = cabi.lib()
+        total = plan.K * plan.n_slots
+        in_rows = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        out_rows = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        k_off = torch.zeros(plan.K + 1, dtype=torch.int64, device=self.device)
+        ws_bytes = L.lg_scan_workspace(total)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        cabi.check(L.lg_kernel_map_pairs(cabi.ptr(plan.nbr), plan.K, plan.n_slots, cabi.ptr(in_rows),
+                                         cabi.ptr(out_rows), cabi.ptr(k_off), cabi.ptr(ws), ws_bytes, cabi.stream()),
+                   "lg_kernel_map_pairs")
+        k_off = k_off.cpu()
+        p = int(k_off[-1])
+        return in_rows[:p], out_rows[:p], k_off

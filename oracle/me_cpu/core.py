@@ -172,6 +172,7 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
                     out.bn.weight, out.bn.bias = module.bn.weight, module.bn.bias
             out.bn.running_mean, out.bn.running_var = module.bn.running_mean, module.bn.running_var
             out.bn.num_batches_tracked = module.bn.num_batches_tracked
+            return out
         for name, child in module.named_children():
             out.add_module(name, cls.convert_sync_batchnorm(child, process_group))
         return out

@@ -1,0 +1,99 @@
+"""CPU: the oracle's voxelisation / coordinate-map / kernel-map conventions.
+MinkowskiEngine is absent, so these are property tests + hand-computed cases (parity unpinned)."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import voxel as ov
+from tests.helpers import random_surface_cloud, random_voxels
+
+
+def test_quantize_is_float32_floor_division():
+    pts = np.array([[0.049999, -0.05, 0.1], [-0.000001, 0.15, -0.1000001]], np.float32)
+    q = ov.quantize_coords(pts, 0.05)
+    ref = np.floor(pts / np.float32(0.05)).astype(np.int32)
+    assert np.array_equal(q, ref)
+    assert q[0, 1] == -1 and q[1, 0] == -1  # negatives floor toward -inf
+    # float32 vs float64 division disagree on some inputs: the oracle must be the float32 one
+    c = np.arange(-1200, 1200)
+    p = (c * 0.05).astype(np.float32)
+    assert (np.floor(p / np.float32(0.05)) != np.floor(p.astype(np.float64) / 0.05)).any()
+
+
+def test_sparse_quantize_known_answer():
+    pts = np.array([[0.01, 0.01, 0.01], [0.12, 0.0, 0.0], [0.02, 0.03, 0.04], [0.11, 0.01, 0.0], [-0.01, 0, 0]], np.float32)
+    labels = np.array([3, 5, 3, 6, 2], np.int32)
+    feats = np.arange(5, dtype=np.float32).reshape(5, 1)
+    q, f, cl, um, inv = ov.sparse_quantize(pts, feats, labels, -1, True, True, False, 0.05)
+    assert q.tolist() == [[0, 0, 0], [2, 0, 0], [-1, 0, 0]]
+    assert um.tolist() == [0, 1, 4] and inv.tolist() == [0, 1, 0, 1, 2]
+    assert f.reshape(-1).tolist() == [0, 1, 4]
+    assert cl.tolist() == [3, -1, 2]  # voxel 1 holds labels 5 and 6 -> ignore
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 400), st.integers(0, 2 ** 31 - 1))
+def test_unique_inverse_properties(n, seed):
+    rng = np.random.default_rng(seed)
+    c = rng.integers(-5, 5, (n, 3)).astype(np.int32)
+    um, inv = ov.unique_first_occurrence(c)
+    assert np.all(np.diff(um) > 0)
+    assert np.array_equal(c[um][inv], c)
+    assert len(np.unique(c, axis=0)) == len(um)
+    # first occurrence: no earlier row holds the same voxel
+    for u, r in enumerate(um):
+        assert not (c[:r] == c[r]).all(1).any()
+
+
+def test_stride_map_and_k2_pairs():
+    rng = np.random.default_rng(0)
+    c = random_voxels(rng, 3000)
+    c2, parent = ov.stride_coords(c, 2)
+    assert np.array_equal(c2[parent][:, 0], c[:, 0])
+    assert np.array_equal(c2[parent][:, 1:], np.floor_divide(c[:, 1:], 2) * 2)
+    maps = ov.kernel_map(c, c2, 2, 1)
+    assert sum(len(i) for i, _ in maps) == len(c)  # each fine voxel in exactly one pair
+    offs = ov.kernel_offsets(2, 1)
+    for k, (i, o) in enumerate(maps):
+        assert np.all(c[i, 1:] - c2[o, 1:] == offs[k])
+        assert np.array_equal(parent[i], o)
+    tmaps = ov.transposed_kernel_map(c, c2, 2, 1)
+    for (i, o), (ti, to) in zip(maps, tmaps):
+        assert sorted(zip(i.tolist(), o.tolist())) == sorted(zip(to.tolist(), ti.tolist()))
+        assert np.all(np.diff(to) > 0)
+
+
+def test_kernel_offsets_order():
+    o3 = ov.kernel_offsets(3, 2)
+    assert o3[0].tolist() == [-2, -2, -2] and o3[1].tolist() == [0, -2, -2] and o3[13].tolist() == [0, 0, 0]
+    assert np.array_equal(o3[::-1], -o3)  # index reversal mirrors the offset (used by dgrad)
+    o2 = ov.kernel_offsets(2, 4)
+    assert o2.tolist() == [[0, 0, 0], [4, 0, 0], [0, 4, 0], [4, 4, 0], [0, 0, 4], [4, 0, 4], [0, 4, 4], [4, 4, 4]]
+
+
+def test_k3_map_symmetry_and_centre():
+    rng = np.random.default_rng(1)
+    c = random_voxels(rng, 2000, span=10)
+    maps = ov.kernel_map(c, c, 3, 1)
+    assert np.array_equal(maps[13][0], np.arange(len(c))) and np.array_equal(maps[13][1], np.arange(len(c)))
+    for k in range(13):
+        a = set(zip(maps[k][0].tolist(), maps[k][1].tolist()))
+        b = set(zip(maps[26 - k][1].tolist(), maps[26 - k][0].tolist()))
+        assert a == b
+
+
+def test_collation_batch_column_first():
+    a = np.array([[1, 2, 3]], np.int32)
+    b = np.array([[4, 5, 6], [7, 8, 9]], np.int32)
+    assert ov.batched_coordinates([a, b]).tolist() == [[0, 1, 2, 3], [1, 4, 5, 6], [1, 7, 8, 9]]
+
+
+def test_synthetic_scan_shapes():
+    from lidog_b200.lidog import synth
+    pts, lab = synth.make_scan(1234, "kitti")
+    assert 100_000 < len(pts) < 140_000 and pts.dtype == np.float32 and lab.min() >= -1 and lab.max() <= 6
+    pts2, _ = synth.make_scan(1234, "kitti")
+    assert np.array_equal(pts, pts2)  # deterministic
+    q = ov.quantize_coords(pts, 0.05)
+    assert np.abs(q[:, :2]).max() < 1200 and q[:, 2].min() >= -200 and q[:, 2].max() < 160
+    pts, _ = synth.make_scan(7, "nuscenes")
+    assert 25_000 < len(pts) < 40_000
