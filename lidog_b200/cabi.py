@@ -60,6 +60,42 @@ SIGNATURES = {
 }
 
 
+# CUDA kernels launched by one call of each entry point (memsets not counted); bench.py multiplies
+# these by the call counts to report `gpu_launches`.
+KERNELS_PER_CALL = {
+    "lg_quantize_points": 1, "lg_coords_unique": 7, "lg_kernel_map": 1, "lg_kernel_map_pairs": 3,
+    "lg_kernel_map_up2": 9, "lg_conv_gemm_simt": 1, "lg_conv_wgrad_simt": 2, "lg_cast_rows": 1,
+    "lg_absmax_scale": 2, "lg_prep_weights": 1, "lg_conv_gemm_tc": 1, "lg_conv_wgrad_tc": 2,
+    "lg_bev_forward": 2, "lg_bev_backward": 3,
+}
+COUNTS: dict = {}
+
+
+class _Counting:
+    """Thin proxy over the CDLL that counts calls per entry point."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._fns = {}
+
+    def __getattr__(self, name):
+        fn = self._fns.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            if name in KERNELS_PER_CALL:
+                def fn(*a, _raw=raw, _name=name):
+                    COUNTS[_name] = COUNTS.get(_name, 0) + 1
+                    return _raw(*a)
+            else:
+                fn = raw
+            self._fns[name] = fn
+        return fn
+
+
+def kernel_launches() -> int:
+    return sum(KERNELS_PER_CALL[k] * v for k, v in COUNTS.items())
+
+
 def lib():
     """Load the shared library once; fail loudly when it is not there."""
     global _LIB
@@ -70,7 +106,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        _LIB = L
+        _LIB = _Counting(L)
     return _LIB
 
 

@@ -25,6 +25,30 @@ CONFIG = {
 }
 
 
+# bench.py instrumentation: per-launch CUDA events + algorithmic FLOPs (2 * pairs * Cin * Cout).
+# A census pass (events=False) counts the pairs of every plan once; timed passes look them up by key.
+PROFILE = {"enabled": False, "events": False, "records": [], "pairs": {}}
+
+
+def _profiled(kernel, plan, cin, cout, launch):
+    if not PROFILE["enabled"]:
+        return launch()
+    if not PROFILE["events"]:
+        if plan.key not in PROFILE["pairs"]:
+            PROFILE["pairs"][plan.key] = plan.count_pairs()
+        out = launch()
+        PROFILE["records"].append(dict(kernel=kernel, key=plan.key, cin=cin, cout=cout,
+                                       flops=2.0 * PROFILE["pairs"][plan.key] * cin * cout))
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = launch()
+    e1.record()
+    PROFILE["records"].append(dict(kernel=kernel, key=plan.key, cin=cin, cout=cout, e0=e0, e1=e1,
+                                   flops=2.0 * PROFILE["pairs"].get(plan.key, 0) * cin * cout))
+    return out
+
+
 def _fmt():
     return {"fp16": cabi.FMT_FP16, "bf16": cabi.FMT_BF16}.get(CONFIG["tc"])
 
@@ -49,9 +73,12 @@ def _gemm_simt(plan, A, W3, N, w_transposed, flip, bias):
 
 def _gemm_tc(plan, A16, B16, N, flip, fmt, out_scale, bias):
     Y = torch.empty((plan.n_out, N), dtype=torch.float32, device=A16.device)
-    cabi.check(cabi.lib().lg_conv_gemm_tc(plan.c, cabi.ptr(A16), A16.shape[1], cabi.ptr(B16), N, flip, fmt,
-                                          cabi.ptr(out_scale), cabi.ptr(bias), cabi.ptr(Y), CONFIG["gather"],
-                                          cabi.stream()), "lg_conv_gemm_tc")
+
+    def launch():
+        cabi.check(cabi.lib().lg_conv_gemm_tc(plan.c, cabi.ptr(A16), A16.shape[1], cabi.ptr(B16), N, flip, fmt,
+                                              cabi.ptr(out_scale), cabi.ptr(bias), cabi.ptr(Y), CONFIG["gather"],
+                                              cabi.stream()), "lg_conv_gemm_tc")
+    _profiled("k_gemm_tc", plan, A16.shape[1], N, launch)
     return Y
 
 
@@ -112,9 +139,10 @@ class SparseConvFunction(torch.autograd.Function):
                 dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
                 ws_bytes = L.lg_conv_wgrad_tc_workspace(p_wgrad.c, cin, cout)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
-                cabi.check(L.lg_conv_wgrad_tc(p_wgrad.c, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt, cabi.ptr(inv),
-                                              cabi.ptr(dw), CONFIG["gather"], cabi.ptr(ws), ws_bytes, cabi.stream()),
-                           "lg_conv_wgrad_tc")
+                _profiled("k_wgrad_tc", p_wgrad, cin, cout, lambda: cabi.check(
+                    L.lg_conv_wgrad_tc(p_wgrad.c, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt, cabi.ptr(inv),
+                                       cabi.ptr(dw), CONFIG["gather"], cabi.ptr(ws), ws_bytes, cabi.stream()),
+                    "lg_conv_wgrad_tc"))
         else:
             x, W3c = ctx.saved_tensors
             if ctx.needs_input_grad[0]:

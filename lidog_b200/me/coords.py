@@ -65,6 +65,11 @@ class GatherPlan:
         self.nbr, self.out_row, self.tile_mask = nbr, out_row, tile_mask
         self.K, self.n_slots, self.n_out, self.n_in, self.k_stride = K, n_slots, n_out, n_in, k_stride
         self.c = cabi.make_plan(nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in)
+        self.key = None
+
+    def count_pairs(self) -> int:
+        """Number of (in, out) pairs of the map (host sync; used by the benchmark census only)."""
+        return int((self.nbr >= 0).sum().item())
 
 
 def _round_up(a, b):
@@ -111,6 +116,7 @@ class CoordinateManager:
         key = (kind, ts_in, ts_out, ksize)
         if key not in self.plans:
             self.plans[key] = getattr(self, "_plan_" + kind)(ts_in, ts_out, ksize)
+            self.plans[key].key = key
         return self.plans[key]
 
     def _neighbor_plan(self, lvl_in: Level, lvl_out: Level, ksize: int, scale: int) -> GatherPlan:

@@ -51,3 +51,31 @@ def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
     std = torch.nn.init.calculate_gain(nonlinearity, a) / math.sqrt(fan)
     with torch.no_grad():
         return tensor.normal_(0, std)
+
+
+def sparse_quantize_batch(points_list, labels_list, quantization_size, ignore_label=-100):
+    """Whole-batch voxelisation (same dict as the product's batched entry point): per-scan
+    first-occurrence order, scans concatenated in list order, batch index in column 0."""
+    coords, umaps, invs, colabs = [], [], [], []
+    row0 = vox0 = 0
+    for b, pts in enumerate(points_list):
+        p = pts.numpy() if isinstance(pts, torch.Tensor) else np.asarray(pts)
+        lab = None if labels_list is None else np.asarray(labels_list[b])
+        if lab is None:
+            q, um, inv = _vox.sparse_quantize(p, quantization_size=quantization_size, return_index=True,
+                                              return_inverse=True)
+            cl = None
+        else:
+            q, cl, um, inv = _vox.sparse_quantize(p, labels=lab, ignore_label=ignore_label,
+                                                  quantization_size=quantization_size, return_index=True,
+                                                  return_inverse=True)
+        coords.append(np.concatenate([np.full((len(q), 1), b, np.int32), q], 1))
+        umaps.append(um + row0)
+        invs.append(inv + vox0)
+        colabs.append(cl)
+        row0 += len(p)
+        vox0 += len(q)
+    out = dict(coords=torch.from_numpy(np.concatenate(coords)), unique_map=torch.from_numpy(np.concatenate(umaps)),
+               inverse_map=torch.from_numpy(np.concatenate(invs)), n=vox0,
+               colabels=None if labels_list is None else torch.from_numpy(np.concatenate(colabs).astype(np.int32)))
+    return out
