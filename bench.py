@@ -40,6 +40,9 @@ def parse():
     p.add_argument("--classes", type=int, default=7)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-baseline-seconds", type=float, default=30.0)
+    p.add_argument("--ncu", action="store_true",
+                   help="profiling run: 1 warm-up + 1 step between cudaProfilerStart/Stop, no e2e / CPU legs "
+                        "(use with ncu --profile-from-start off; numbers printed under ncu are not bench values)")
     return p.parse_args()
 
 
@@ -49,7 +52,9 @@ def peaks():
         d = json.load(open(path))
         return dict(hbm_gbs=d["hbm_gbs"], tf_sustained=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"],
                     source="measured")
-    return dict(hbm_gbs=6650.0, tf_sustained=1400.0, tf_burst=1590.0, source="fallback")
+    # MEASURED_PEAKS.json is driver-written and git-ignored; when this checkout lost it, use the values the
+    # driver measured on this pool at the start of round 1 (recorded in SURVEY.md section 0).
+    return dict(hbm_gbs=6441.9, tf_sustained=1407.8, tf_burst=1669.9, source="measured (round-1 driver values recorded in SURVEY.md)")
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -235,6 +240,14 @@ def run_ours(args):
         lab = [l.to(dev, non_blocking=True) for l in host_lab]
         return float(trainer.training_step(pts, lab).item())  # D2H read of the loss
 
+    if args.ncu:
+        resident_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        resident_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     for _ in range(max(args.warmup, 3)):
         resident_step()
     # census (untimed): algorithmic FLOPs of every sparse-conv launch of one step
