@@ -318,7 +318,7 @@ def run_ours(args):
                            "points_per_step_per_gpu": n_points, "global_batch": world * args.batch,
                            "parallelism": f"dp{world}" + (" (DDP + SyncBN over NCCL)" if world > 1 else ""),
                            "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",
-                           "conv_operands": meconv.CONFIG["tc"], "gather": "tma_gather4" if meconv.CONFIG["gather"] else "cp.async"},
+                           "conv_operands": meconv.CONFIG["tc"], "gather": {0: "cp.async v1", 1: "tma_gather4 v1", 2: "cp.async+mbarrier super-tile v2"}[meconv.CONFIG["gather"]]},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "sparse_conv_ms_per_scan": conv_ms / args.batch, "kernels": kernels,
                 "cpu_baseline": cpu}

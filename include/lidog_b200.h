@@ -151,7 +151,9 @@ int lg_prep_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout, void* 
  * utils/models/minkunet_bev.py:57-123):  Y[out_row[s], :] = out_scale * sum_k A16[nbr[k][s], :] @ B16[wk]^T
  * A16 [n_in][Ck] and B16 [K][N][Ck] are 16-bit (fmt), Ck % 32 == 0, N % 16 == 0, N <= 512.
  * out_scale: nullable device float (undoes lg_absmax_scale).  bias nullable [N].
- * gather_mode: 1 = TMA (tile::gather4 rows + tiled weight slabs), 0 = cp.async with zero fill. */
+ * gather_mode: 2 = super-tile pipeline (cp.async row gathers arriving on mbarriers, weight panels by TMA,
+ *              up to 8 row tiles accumulating in TMEM per weight load; default, csrc/conv_tc2.cu);
+ *              1 = first-generation kernel with TMA tile::gather4 rows; 0 = first generation, cp.async. */
 int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t Ck, const void* B16, int32_t N, int32_t flip_k,
                     int32_t fmt, const float* out_scale, const float* bias, float* Y, int32_t gather_mode,
                     void* stream);

@@ -161,6 +161,127 @@ __global__ void __launch_bounds__(256)
   dW[i] = out_scale ? s * out_scale[0] : s;
 }
 
+
+// ------------------------------------------------------------------------------------ Cin == 1 stem
+// conv0p1s1 of MinkUNet34 (utils/models/minkunet_bev.py:57: kernel 5, 1 -> 32 channels, 125 offsets) is a
+// scalar gather, not a GEMM: Y[o][:] = sum_k x[nbr[k][o]] * W[k][:].  Thread = output row, W in shared
+// memory (broadcast reads), result rows transposed through shared memory for coalesced stores.
+constexpr int C1_N = 32;
+
+__global__ void __launch_bounds__(128)
+    k_conv_c1_fwd(lgConvPlan plan, const float* __restrict__ X, const float* __restrict__ W, int flip_k,
+                  const float* __restrict__ bias, float* __restrict__ Y) {
+  extern __shared__ float c1_sm[];
+  float* Ws = c1_sm;                                   // [K][32]
+  float* Ts = c1_sm + plan.kernel_volume * C1_N;       // [4 warps][32][33]
+  const int K = plan.kernel_volume;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < K * C1_N; e += 128) {
+    const int k = e / C1_N;
+    Ws[e] = W[(flip_k ? (K - 1 - k) : k) * C1_N + (e - k * C1_N)];
+  }
+  __syncthreads();
+  const int64_t n_tiles = plan.n_slots / TM;
+  float* Tw = Ts + warp * 32 * 33;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * TM + threadIdx.x;
+    float acc[C1_N];
+#pragma unroll
+    for (int j = 0; j < C1_N; ++j) acc[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t m = __ldg(plan.tile_mask + tile * plan.mask_words + (k >> 5));
+      if (!((m >> (k & 31)) & 1u)) continue;
+      const int nb = __ldg(plan.nbr + (int64_t)k * plan.k_stride + s);
+      if (nb >= 0) {
+        const float x = __ldg(X + nb);
+        const float4* w4 = reinterpret_cast<const float4*>(Ws + k * C1_N);
+#pragma unroll
+        for (int j = 0; j < C1_N / 4; ++j) {
+          const float4 w = w4[j];
+          acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+    // transpose through shared memory: lane = row -> lane = channel
+#pragma unroll
+    for (int j = 0; j < C1_N; ++j) Tw[lane * 33 + j] = acc[j];
+    __syncwarp();
+    const float b = bias ? bias[lane] : 0.f;
+    const int64_t s0 = tile * TM + warp * 32;
+    for (int r = 0; r < 32; ++r) {
+      int64_t row = plan.out_row ? (int64_t)plan.out_row[s0 + r] : s0 + r;
+      if (row >= 0 && row < plan.n_out) Y[row * C1_N + lane] = Tw[r * 33 + lane] + b;
+    }
+    __syncwarp();
+  }
+}
+
+// dW[k][co] = sum_o x[nbr[k][o]] * dY[o][co]: lane = output channel, acc[k] in registers, the gathered
+// scalars of a 32-row window staged in shared memory; one partial [K][32] per CTA, reduced in fixed order.
+constexpr int C1_KMAX = 128;
+
+__global__ void __launch_bounds__(256, 1)
+    k_conv_c1_wgrad(lgConvPlan plan, const float* __restrict__ X, const float* __restrict__ dY,
+                    float* __restrict__ partial) {
+  __shared__ __align__(16) float xs[32][C1_KMAX];
+  __shared__ float red[C1_KMAX][C1_N];
+  const int K = plan.kernel_volume;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[C1_KMAX];
+#pragma unroll
+  for (int k = 0; k < C1_KMAX; ++k) acc[k] = 0.f;
+  const int64_t n_win = plan.n_slots / 32;
+  for (int64_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+    const int64_t s0 = win * 32;
+    __syncthreads();
+    for (int e = threadIdx.x; e < C1_KMAX * 32; e += 256) {
+      const int k = e >> 5, r = e & 31;
+      float v = 0.f;
+      if (k < K) {
+        const int nb = __ldg(plan.nbr + (int64_t)k * plan.k_stride + s0 + r);
+        if (nb >= 0) v = __ldg(X + nb);
+      }
+      xs[r][k] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = warp; r < 32; r += 8) {
+      const int64_t s = s0 + r;
+      int64_t row = plan.out_row ? (int64_t)plan.out_row[s] : s;
+      if (row < 0 || row >= plan.n_out) continue;
+      const float dy = __ldg(dY + row * C1_N + lane);
+      const float4* x4 = reinterpret_cast<const float4*>(&xs[r][0]);
+#pragma unroll
+      for (int j = 0; j < C1_KMAX / 4; ++j) {
+        const float4 x = x4[j];
+        acc[4 * j + 0] = fmaf(x.x, dy, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(x.y, dy, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(x.z, dy, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(x.w, dy, acc[4 * j + 3]);
+      }
+    }
+  }
+  // fixed-order reduction over the 8 warps
+  for (int w = 0; w < 8; ++w) {
+    __syncthreads();
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < C1_KMAX; ++k) red[k][lane] = (w == 0 ? 0.f : red[k][lane]) + acc[k];
+    }
+  }
+  __syncthreads();
+  float* P = partial + (int64_t)blockIdx.x * K * C1_N;
+  for (int e = threadIdx.x; e < K * C1_N; e += 256) P[e] = red[e >> 5][e & 31];
+}
+
+static int c1_wgrad_blocks(const lgConvPlan* plan) {
+  const int64_t n_win = plan->n_slots / 32;
+  return (int)(n_win < 296 ? (n_win > 0 ? n_win : 1) : 296);
+}
+
 int wgrad_chunks(const lgConvPlan* plan, int* tiles_per_chunk) {
   const int64_t n_tiles = plan->n_slots / TM;
   int64_t want = 592 / (plan->kernel_volume > 0 ? plan->kernel_volume : 1);
@@ -201,6 +322,14 @@ extern "C" int lg_conv_gemm_simt(const lgConvPlan* plan, const float* A, int32_t
   LG_CHECK_ARG(Ca >= 1 && N >= 1, "lg_conv_gemm_simt: bad channel counts");
   if (plan->n_slots == 0) return LG_OK;
   LG_CHECK_ARG(A && W && Y, "lg_conv_gemm_simt: null pointer");
+  if (Ca == 1 && N == C1_N && !w_transposed && plan->kernel_volume <= C1_KMAX) {
+    const int64_t n_tiles = plan->n_slots / TM;
+    const size_t smem = ((size_t)plan->kernel_volume * C1_N + 4 * 32 * 33) * sizeof(float);
+    const unsigned blocks = (unsigned)(n_tiles < 148 * 8 ? n_tiles : 148 * 8);
+    k_conv_c1_fwd<<<blocks, 128, smem, (cudaStream_t)stream>>>(*plan, A, W, flip_k, bias, Y);
+    LG_LAUNCH_OK();
+    return LG_OK;
+  }
   dim3 grid((unsigned)(plan->n_slots / TM), (unsigned)ceil_div(N, TN));
   k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(*plan, A, Ca, W, N, w_transposed, flip_k, bias, Y);
   LG_LAUNCH_OK();
@@ -211,6 +340,7 @@ extern "C" size_t lg_conv_wgrad_workspace(const lgConvPlan* plan, int32_t Ca, in
   if (!plan) return 0;
   int tpc;
   int chunks = wgrad_chunks(plan, &tpc);
+  if (Ca == 1 && Cb == C1_N && chunks < c1_wgrad_blocks(plan)) chunks = c1_wgrad_blocks(plan);
   return (size_t)chunks * plan->kernel_volume * Ca * Cb * sizeof(float) + 256;
 }
 
@@ -227,6 +357,12 @@ extern "C" int lg_conv_wgrad_simt(const lgConvPlan* plan, const float* X_in, int
   }
   LG_CHECK_ARG(workspace && workspace_bytes >= lg_conv_wgrad_workspace(plan, Cin, Cout),
                "lg_conv_wgrad_simt: workspace too small");
+  if (Cin == 1 && Cout == C1_N && plan->kernel_volume <= C1_KMAX) {
+    const int blocks = c1_wgrad_blocks(plan);
+    k_conv_c1_wgrad<<<blocks, 256, 0, stream>>>(*plan, X_in, dY_out, (float*)workspace);
+    LG_LAUNCH_OK();
+    return launch_reduce_partials((const float*)workspace, blocks, n_elems, nullptr, dW, stream);
+  }
   int tpc;
   const int chunks = wgrad_chunks(plan, &tpc);
   dim3 grid((unsigned)plan->kernel_volume, (unsigned)chunks,

@@ -26,6 +26,12 @@ namespace lg {
 
 int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
                            cudaStream_t stream);
+// second-generation pipeline (conv_tc2.cu), gather_mode 2
+int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void* B16, int N, int flip_k, int fmt,
+                    const float* out_scale, const float* bias, float* Y, cudaStream_t stream);
+size_t wgrad_tc2_workspace(const lgConvPlan* plan, int Cin, int Cout);
+int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const void* dY16, int Cout, int fmt,
+                     const float* out_scale, float* dW, void* workspace, cudaStream_t stream);
 
 using namespace ptx;
 
@@ -508,6 +514,17 @@ static int tc_runtime_init() {
   return LG_OK;
 }
 
+int tc_make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  return make_tmap(m, base, rows, cols, box_rows);
+}
+int tc_runtime(int* sm_count, int** err_word) {
+  int rc = tc_runtime_init();
+  if (rc) return rc;
+  *sm_count = g_sm_count;
+  *err_word = g_err_word;
+  return LG_OK;
+}
+
 int wgrad_tc_chunks(const lgConvPlan* plan, int m_blocks, int* tiles_per_chunk) {
   const int64_t n_tiles = plan->n_slots / LG_TILE_ROWS;
   int64_t want = 592 / ((int64_t)plan->kernel_volume * m_blocks);
@@ -546,6 +563,8 @@ extern "C" int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t 
   }
   LG_CHECK_ARG(fmt == LG_FMT_BF16 || fmt == LG_FMT_FP16, "lg_conv_gemm_tc: bad format");
   LG_CHECK_ARG(A16 && B16 && Y, "lg_conv_gemm_tc: null pointer");
+  if (gather_mode == 2)
+    return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, stream);
   rc = tc_runtime_init();
   if (rc) return rc;
   GemmArgs g;
@@ -592,7 +611,9 @@ extern "C" size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin
   if (!plan) return 0;
   int tpc;
   const int chunks = wgrad_tc_chunks(plan, (Cin + 127) / 128, &tpc);
-  return (size_t)chunks * plan->kernel_volume * Cin * Cout * sizeof(float) + 256;
+  const size_t v1 = (size_t)chunks * plan->kernel_volume * Cin * Cout * sizeof(float) + 256;
+  const size_t v2 = (Cout >= 32 && Cout <= 256) ? wgrad_tc2_workspace(plan, Cin, Cout) : 0;
+  return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const void* dY16, int32_t Cout,
@@ -608,6 +629,7 @@ extern "C" int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t
   LG_CHECK_ARG(fmt == LG_FMT_BF16 || fmt == LG_FMT_FP16, "lg_conv_wgrad_tc: bad format");
   LG_CHECK_ARG(X16 && dY16 && dW && workspace, "lg_conv_wgrad_tc: null pointer");
   LG_CHECK_ARG(workspace_bytes >= lg_conv_wgrad_tc_workspace(plan, Cin, Cout), "lg_conv_wgrad_tc: workspace too small");
+  if (gather_mode == 2) return launch_wgrad_tc2(plan, X16, Cin, dY16, Cout, fmt, out_scale, dW, workspace, stream);
   rc = tc_runtime_init();
   if (rc) return rc;
   WgradArgs g;

@@ -1,0 +1,823 @@
+// Sparse convolution on tcgen05, second-generation pipeline (gather_mode 2, the default).
+//
+// Measured on B200 (profiles/r01_conv_bench_v1.txt): tile::gather4 TMA moves 256 B per instruction and
+// sustains ~100 SM cycles per instruction, 2.7x slower than LDGSTS (cp.async) row gathers; and a
+// producer that waits for its own copies keeps only two stages in flight.  This pipeline therefore
+//   * gathers operand rows with cp.async (16 B per lane, 4 lanes per 64-byte row segment, so every
+//     request is a full 32 B sector pair) and lets the copies themselves arrive on the stage's
+//     mbarrier (cp.async.mbarrier.arrive.noinc): producers never wait for data, the whole ring is in
+//     flight;
+//   * gives each of the 4 producer warps whole stages (unit u -> warp u % 4), so the index fetch of
+//     one stage overlaps the copies of three others;
+//   * forward / dgrad (k_gemm2): a CTA owns a SUPER-TILE of T row tiles whose T accumulators live in
+//     TMEM together (T * N <= 512 columns); the loop runs kernel offset outermost, so one TMA load of
+//     the weight panel W[k] feeds up to T gathered tiles (weight traffic / T);
+//   * wgrad (k_wgrad2): a CTA owns a group of G kernel offsets (G * Cout <= 512 TMEM columns) and a
+//     chunk of tiles; the dY tile is staged once and reused by every offset of the group.
+// Shared-memory operand tiles keep the SWIZZLE_64B layout of conv_tc.cu (64-byte rows = 32 channels).
+// Results are deterministic: every output row / weight element is written once in a fixed order.
+// Reference contract: MinkowskiConvolution(+Transpose) forward/backward, utils/models/minkunet_bev.py:57-123.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace lg {
+
+int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
+                           cudaStream_t stream);
+int tc_make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows);
+int tc_runtime(int* sm_count, int** err_word);
+
+namespace v2 {
+using namespace ptx;
+
+// LIDOG_DBG & 8: CTA 0 accumulates the cycles each role spends waiting (read back by lg_debug_profile)
+__device__ long long g_prof[16];
+#define PROF_T0() long long _t0 = clock64()
+#define PROF_ADD(slot) do { if (prof) { long long _t1 = clock64(); pacc[slot] += _t1 - _t0; _t0 = _t1; } } while (0)
+#define PROF_FLUSH(lo, hi) do { if (prof) for (int _i = lo; _i <= hi; ++_i) g_prof[_i] += pacc[_i]; } while (0)
+
+constexpr int kRowB = 64;            // bytes per smem operand row (32 x 16-bit)
+constexpr int kSub = 128 * kRowB;    // one [128 rows x 32 channels] sub-tile = 8 KB
+constexpr int kEpiWarps = 4;         // warps 0..3
+constexpr int kMmaWarp = 4;
+constexpr int kBWarp = 5;            // weight-panel TMA producer (forward) / unused (wgrad)
+constexpr int kProdWarp0 = 6;
+constexpr int kProdWarps = 4;        // warps 6..9
+constexpr int kIdxWarp = kProdWarp0 + kProdWarps;  // warp 10: row-id ring (bulk copies of 512 B id rows)
+constexpr int kThreads = (kIdxWarp + 1) * 32;
+constexpr int kIdxSlotBytes = LG_TILE_ROWS * 4;
+
+__device__ __forceinline__ uint32_t sw64(uint32_t r, uint32_t j) { return r * kRowB + ((j ^ ((r >> 1) & 3u)) << 4); }
+
+// 1D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t saddr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tile-mask words of the (<= 8) tiles of a super-tile, kept in registers; reloaded every 32 offsets
+struct TileMasks {
+  uint32_t w[8];
+};
+__device__ __forceinline__ void load_masks(TileMasks& tm, const lgConvPlan& p, int64_t tile0, int nt, int word) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) tm.w[t] = (t < nt) ? __ldg(p.tile_mask + (tile0 + t) * p.mask_words + word) : 0u;
+}
+__device__ __forceinline__ uint32_t present_bits(const TileMasks& tm, int k) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) m |= ((tm.w[t] >> (k & 31)) & 1u) << t;
+  return m;
+}
+__device__ __forceinline__ uint32_t any_mask(const lgConvPlan& p, int64_t tile0, int nt) {
+  uint32_t m = 0;
+  for (int t = 0; t < nt; ++t) {
+    uint32_t w = 0;
+    for (int i = 0; i < p.mask_words; ++i) w |= __ldg(p.tile_mask + (tile0 + t) * p.mask_words + i);
+    m |= (w != 0 ? 1u : 0u) << t;
+  }
+  return m;
+}
+
+// Gather 128 rows x (PC * 32) channels of a row-major 16-bit matrix into `dst` (PC sub-tiles of 8 KB,
+// SWIZZLE_64B).  One warp does the whole stage: lane = (row % 8, 16-byte piece), 16 rows per lane
+// (rows[i] = id of row 8*i + lane/4, negative = zero fill); PC copies per row are issued back to back;
+// byte offsets stay in 32 bits (host checks rows * ld * 2 < 2^32).
+template <int PC>
+__device__ __forceinline__ void gather_rows(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t ld_bytes,
+                                            const int (&rows)[16], int lane) {
+  const int piece = lane & 3, rsub = lane >> 2;
+  const uint8_t* base = src + piece * 16;
+  uint8_t* d0 = dst + sw64(rsub, piece);  // row 8*i + rsub sits 512*i bytes further (same swizzle phase)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = rows[i];
+    const bool ok = row >= 0;
+    const uint8_t* s = base + (size_t)((uint32_t)(ok ? row : 0) * ld_bytes);
+#pragma unroll
+    for (int c = 0; c < PC; ++c) cp_async16(d0 + i * 512 + c * kSub, s + c * 64, ok);
+  }
+}
+
+__device__ __forceinline__ void gather_stage(uint8_t* dst, const uint16_t* src, int ld, int col0, int pc,
+                                             const int (&rows)[16], int lane) {
+  const uint8_t* s = reinterpret_cast<const uint8_t*>(src + col0);
+  const uint32_t ldb = (uint32_t)ld * 2u;
+  switch (pc) {
+    case 1: gather_rows<1>(dst, s, ldb, rows, lane); break;
+    case 2: gather_rows<2>(dst, s, ldb, rows, lane); break;
+    case 3: gather_rows<3>(dst, s, ldb, rows, lane); break;
+    default: gather_rows<4>(dst, s, ldb, rows, lane); break;
+  }
+}
+
+// row ids of a stage from the shared-memory id ring (filled by the id warp's bulk copies)
+__device__ __forceinline__ void ids_from_ring(int (&rows)[16], uint32_t slot_saddr, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) rows[i] = lds32(slot_saddr + 4 * (8 * i + (lane >> 2)));
+}
+
+// ------------------------------------------------------------------------------------ forward / dgrad
+struct Gemm2Args {
+  lgConvPlan plan;
+  const uint16_t* A;  // [n_in][Ck]
+  float* Y;           // [n_out][N]
+  const float* out_scale;
+  const float* bias;
+  int Ck, N, n_blk, flip, umma_fmt;
+  int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs
+  int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
+  int64_t n_tiles, n_super;
+  int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stageA = g.pc * kSub, stageB = g.pc * g.n_blk * kRowB;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + (size_t)g.sa * stageA;
+  uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
+  const int ni = 8 * g.np;
+  uint64_t* fullA = (uint64_t*)(smI + (size_t)ni * kIdxSlotBytes);
+  uint64_t* emptyA = fullA + g.sa;
+  uint64_t* fullB = emptyA + g.sa;
+  uint64_t* emptyB = fullB + g.sb;
+  uint64_t* fullI = emptyB + g.sb;
+  uint64_t* emptyI = fullI + ni;
+  uint64_t* acc_full = emptyI + ni;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 1);
+  const int n0 = blockIdx.y * g.n_blk;
+  const int K = g.plan.kernel_volume;
+  const bool prof = (g.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.sa; ++s) {
+      mbar_init(&fullA[s], 32);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < g.sb; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < ni; ++s) {
+      mbar_init(&fullI[s], 1);
+      mbar_init(&emptyI[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kEpiWarps * 32);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+  if (warp == kBWarp && lane == 0) prefetch_tmap(&tmB);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kIdxWarp) {
+    // ===================================================================== id ring (one thread, runs ahead)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t iphase = 0;
+      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+        const int64_t tile0 = st * g.T;
+        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+        TileMasks tm;
+        for (int k = 0; k < K; ++k) {
+          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+          const uint32_t m = present_bits(tm, k);
+          if (!m) continue;
+          for (int p = 0; p < g.n_panels; ++p) {
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+              const int t = __ffs(mm) - 1;
+              mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
+              mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
+              bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
+                            g.plan.nbr + (int64_t)k * g.plan.k_stride + (tile0 + t) * LG_TILE_ROWS, kIdxSlotBytes,
+                            &fullI[slot]);
+              if (++slot == ni) {
+                slot = 0;
+                iphase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= kProdWarp0) {
+    // ===================================================================== A producers (cp.async gather)
+    const int pw = warp - kProdWarp0;
+    int stage = 0, turn = 0, slot = 0;
+    uint32_t phase = 0, iphase = 0;
+    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+      const int64_t tile0 = st * g.T;
+      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      TileMasks tm;
+      for (int k = 0; k < K; ++k) {
+        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        const uint32_t m = present_bits(tm, k);
+        if (!m) continue;
+        for (int p = 0; p < g.n_panels; ++p) {
+          for (int t = 0; t < nt; ++t) {
+            if (!((m >> t) & 1u)) continue;
+            if (turn == pw) {
+              PROF_T0();
+              int rows[16];
+              mbar_wait(&fullI[slot], iphase, g.err, 8);
+              ids_from_ring(rows, smem_u32(smI) + slot * kIdxSlotBytes, lane);
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(&emptyI[slot]);
+                mbar_wait(&emptyA[stage], phase ^ 1, g.err, 1);
+              }
+              __syncwarp();
+              if (pw == 0) PROF_ADD(0);
+              if (!(g.dbg & 2))
+                gather_stage(smA + (size_t)stage * stageA, g.A, g.Ck, p * g.pc * 32, g.pc, rows, lane);
+              cp_async_arrive_noinc(&fullA[stage]);
+              if (pw == 0) PROF_ADD(1);
+            }
+            turn = (turn + 1 == g.np) ? 0 : turn + 1;
+            if (++stage == g.sa) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (++slot == ni) {
+              slot = 0;
+              iphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kBWarp) {
+    // ===================================================================== B producer (weight panels, TMA)
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bphase = 0;
+      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+        const int64_t tile0 = st * g.T;
+        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+        TileMasks tm;
+        for (int k = 0; k < K; ++k) {
+          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+          if (!present_bits(tm, k)) continue;
+          const int wk = g.flip ? (K - 1 - k) : k;
+          for (int p = 0; p < g.n_panels; ++p) {
+            PROF_T0();
+            mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 2);
+            PROF_ADD(2);
+            if (g.dbg & 1) {
+              mbar_arrive(&fullB[bs]);
+            } else {
+              mbar_arrive_expect_tx(&fullB[bs], (uint32_t)stageB);
+              uint8_t* dst = smB + (size_t)bs * stageB;
+              for (int c = 0; c < g.pc; ++c)
+                tma_load_2d(dst + c * g.n_blk * kRowB, &tmB, (p * g.pc + c) * 32, wk * g.N + n0, &fullB[bs]);
+            }
+            if (++bs == g.sb) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================================================== MMA issuer (one thread)
+    // The whole role runs in lane 0: descriptors are a constant high word plus (address >> 4), so a unit
+    // costs a barrier wait, two adds per MMA and a commit -- the tensor pipe, not this thread, sets the pace.
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(g.umma_fmt, 0, 0, LG_TILE_ROWS, g.n_blk);
+      const uint64_t desc_hi = make_smem_desc(0, 16, 8 * kRowB, kLayoutSw64);
+      const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
+      const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
+      const uint32_t b_sub16 = (uint32_t)(g.n_blk * kRowB) >> 4;
+      const int pc = g.pc;
+      int stage = 0, bs = 0;
+      uint32_t phase = 0, bphase = 0, it = 0;
+      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+        const int64_t tile0 = st * g.T;
+        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+        if (!any_mask(g.plan, tile0, nt)) continue;
+        PROF_T0();
+        mbar_wait(acc_empty, (it & 1) ^ 1, g.err, 3);
+        PROF_ADD(3);
+        ++it;
+        tc_fence_after();
+        uint32_t started = 0;
+        TileMasks tm;
+        for (int k = 0; k < K; ++k) {
+          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+          const uint32_t m = present_bits(tm, k);
+          if (!m) continue;
+          for (int p = 0; p < g.n_panels; ++p) {
+            mbar_wait(&fullB[bs], bphase, g.err, 4);
+            PROF_ADD(4);
+            const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+              const int t = __ffs(mm) - 1;
+              PROF_ADD(7);
+              mbar_wait(&fullA[stage], phase, g.err, 5);
+              PROF_ADD(5);
+              if (!(g.dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
+              tc_fence_after();
+              PROF_ADD(10);
+              const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
+              const uint32_t d_tmem = tmem_base + t * g.n_blk;
+              uint32_t acc = (started >> t) & 1u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < pc && !(g.dbg & 4)) {
+                  umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, acc);
+                  umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
+                  acc = 1u;
+                }
+              }
+              PROF_ADD(6);
+              umma_commit(&emptyA[stage]);
+              PROF_ADD(11);
+              started |= 1u << t;
+              if (++stage == g.sa) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            umma_commit(&emptyB[bs]);
+            if (++bs == g.sb) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+        }
+        umma_commit(acc_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 0..3)
+    const float scale = g.out_scale ? g.out_scale[0] : 1.f;
+    uint32_t it = 0;
+    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+      const int64_t tile0 = st * g.T;
+      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      const uint32_t am = any_mask(g.plan, tile0, nt);
+      PROF_T0();
+      if (am) {
+        mbar_wait(acc_full, it & 1, g.err, 6);
+        ++it;
+        tc_fence_after();
+      }
+      if (warp == 0) PROF_ADD(8);
+      for (int t = 0; t < nt; ++t) {
+        const int64_t s = (tile0 + t) * LG_TILE_ROWS + warp * 32 + lane;
+        int64_t row = g.plan.out_row ? (int64_t)g.plan.out_row[s] : s;
+        const bool row_ok = row >= 0 && row < g.plan.n_out;
+        float* yrow = g.Y + (row_ok ? row : 0) * g.N + n0;
+        if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
+          if (row_ok)
+            for (int n = 0; n < g.n_blk; n += 4) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
+              *reinterpret_cast<float4*>(yrow + n) = o;
+            }
+          continue;
+        }
+        const uint32_t taddr = tmem_base + t * g.n_blk + ((uint32_t)(warp * 32) << 16);
+        for (int n = 0; n < g.n_blk; n += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + n, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * q + 0]) * scale;
+              o.y = __uint_as_float(v[4 * q + 1]) * scale;
+              o.z = __uint_as_float(v[4 * q + 2]) * scale;
+              o.w = __uint_as_float(v[4 * q + 3]) * scale;
+              if (g.bias) {
+                const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
+                o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+              }
+              *reinterpret_cast<float4*>(yrow + n + 4 * q) = o;
+            }
+          }
+        }
+      }
+      if (am) {
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+      }
+      if (warp == 0) PROF_ADD(9);
+    }
+  }
+  if (warp == kProdWarp0) PROF_FLUSH(0, 1);
+  if (warp == kBWarp) PROF_FLUSH(2, 2);
+  if (warp == kMmaWarp) PROF_FLUSH(3, 7);
+  if (warp == kMmaWarp) PROF_FLUSH(10, 11);
+  if (warp == 0) PROF_FLUSH(8, 9);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+// dW[k] (Cin x Cout) = sum_s X16[nbr[k][s], :]^T dY16[out_row[s] (or s), :].
+// CTA = (group of G kernel offsets, 128-channel block of Cin, chunk of tiles).
+// A stage: gathered X rows [128 pairs x 4 sub-blocks of 32 channels]; B stage: dY rows [128 pairs x Cout].
+struct Wgrad2Args {
+  lgConvPlan plan;
+  const uint16_t* X;
+  const uint16_t* dY;
+  float* partial;  // [chunks][K][Cin][Cout]
+  int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np;
+  int64_t n_tiles;
+  int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x / g.m_blocks, mb = blockIdx.x % g.m_blocks;
+  const int chunk = blockIdx.y;
+  const int K = g.plan.kernel_volume;
+  const int k0 = grp * g.G, k1 = min(K, k0 + g.G);
+  const int m0 = mb * 128;
+  const int na = min(4, (g.Cin - m0) / 32);  // real 32-channel sub-blocks of the A operand
+  const int nb = g.Cout / 32;
+  const int stageA = 4 * kSub, stageB = nb * kSub;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + (size_t)g.sa * stageA;
+  uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
+  const int ni = 8 * g.np;
+  uint64_t* fullA = (uint64_t*)(smI + (size_t)ni * kIdxSlotBytes);
+  uint64_t* emptyA = fullA + g.sa;
+  uint64_t* fullB = emptyA + g.sa;
+  uint64_t* emptyB = fullB + g.sb;
+  uint64_t* fullI = emptyB + g.sb;
+  uint64_t* emptyI = fullI + ni;
+  uint64_t* done = emptyI + ni;
+  uint32_t* tmem_slot = (uint32_t*)(done + 1);
+  const int64_t t0 = (int64_t)chunk * g.tiles_per_chunk;
+  const int64_t t1 = min(t0 + g.tiles_per_chunk, g.n_tiles);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.sa; ++s) {
+      mbar_init(&fullA[s], 32);
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < g.sb; ++s) {
+      mbar_init(&fullB[s], 32);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < ni; ++s) {
+      mbar_init(&fullI[s], 1);
+      mbar_init(&emptyI[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // bit j of group_mask(tile) = offset k0 + j present in the tile
+  auto group_mask = [&](int64_t tile) -> uint32_t {
+    const uint32_t* mw = g.plan.tile_mask + tile * g.plan.mask_words;
+    const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;
+    const uint64_t bits = (uint64_t)__ldg(mw + w0) | (w1 != w0 ? (uint64_t)__ldg(mw + w1) << 32 : 0ull);
+    return (uint32_t)(bits >> (k0 & 31)) & ((1u << (k1 - k0)) - 1u);
+  };
+
+  if (warp == kIdxWarp) {
+    // ---------------------------------------------------------------- id ring (one thread, runs ahead)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t iphase = 0;
+      for (int64_t tile = t0; tile < t1; ++tile) {
+        for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
+          const int k = k0 + __ffs(mm) - 1;
+          mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 16);
+          mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
+          bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
+                        g.plan.nbr + (int64_t)k * g.plan.k_stride + tile * LG_TILE_ROWS, kIdxSlotBytes, &fullI[slot]);
+          if (++slot == ni) {
+            slot = 0;
+            iphase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= kProdWarp0) {
+    // ---------------------------------------------------------------- X producers
+    const int pw = warp - kProdWarp0;
+    int stage = 0, turn = 0, slot = 0;
+    uint32_t phase = 0, iphase = 0;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+      for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
+        if (turn == pw) {
+          int rows[16];
+          mbar_wait(&fullI[slot], iphase, g.err, 17);
+          ids_from_ring(rows, smem_u32(smI) + slot * kIdxSlotBytes, lane);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&emptyI[slot]);
+            mbar_wait(&emptyA[stage], phase ^ 1, g.err, 11);
+          }
+          __syncwarp();
+          gather_stage(smA + (size_t)stage * stageA, g.X, g.Cin, m0, na, rows, lane);
+          cp_async_arrive_noinc(&fullA[stage]);
+        }
+        turn = (turn + 1 == g.np) ? 0 : turn + 1;
+        if (++stage == g.sa) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++slot == ni) {
+          slot = 0;
+          iphase ^= 1;
+        }
+      }
+    }
+  } else if (warp == kBWarp) {
+    // ---------------------------------------------------------------- dY producer (one warp, whole tiles)
+    int bs = 0;
+    uint32_t bphase = 0;
+    const int lim = (int)g.plan.n_out;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+      if (!group_mask(tile)) continue;
+      int rows[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int sl = (int)(tile * LG_TILE_ROWS) + 8 * i + (lane >> 2);
+        const int r = g.plan.out_row ? __ldg(g.plan.out_row + sl) : sl;
+        rows[i] = (r < lim) ? r : -1;
+      }
+      if (lane == 0) mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 12);
+      __syncwarp();
+      uint8_t* dst = smB + (size_t)bs * stageB;
+      for (int c0 = 0; c0 < nb; c0 += 4)
+        gather_stage(dst + c0 * kSub, g.dY, g.Cout, c0 * 32, min(4, nb - c0), rows, lane);
+      cp_async_arrive_noinc(&fullB[bs]);
+      if (++bs == g.sb) {
+        bs = 0;
+        bphase ^= 1;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(g.umma_fmt, 1, 1, 128, g.Cout);
+      // MN-major SWIZZLE_64B: LBO = pitch between 32-channel sub-blocks, SBO = 8 rows * 64 B
+      const uint64_t desc_hi = make_smem_desc(0, kSub, 8 * kRowB, kLayoutSw64);
+      const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
+      const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
+      int stage = 0, bs = 0;
+      uint32_t phase = 0, bphase = 0, started = 0;
+      for (int64_t tile = t0; tile < t1; ++tile) {
+        const uint32_t m = group_mask(tile);
+        if (!m) continue;
+        mbar_wait(&fullB[bs], bphase, g.err, 13);
+        fence_proxy_async();
+        const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
+        for (uint32_t mm = m; mm; mm &= mm - 1) {
+          const int j = __ffs(mm) - 1;
+          mbar_wait(&fullA[stage], phase, g.err, 14);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
+          const uint32_t d_tmem = tmem_base + j * g.Cout;
+          umma_f16(d_tmem, da0, db0, idesc, (started >> j) & 1u);
+#pragma unroll
+          for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
+            umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
+          umma_commit(&emptyA[stage]);
+          started |= 1u << j;
+          if (++stage == g.sa) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&emptyB[bs]);
+        if (++bs == g.sb) {
+          bs = 0;
+          bphase ^= 1;
+        }
+      }
+      if (started)
+        umma_commit(done);
+      else
+        mbar_arrive(done);
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue: lane = input channel
+    uint32_t started = 0;
+    for (int64_t tile = t0; tile < t1; ++tile) started |= group_mask(tile);
+    const int ci = m0 + warp * 32 + lane;
+    mbar_wait(done, 0, g.err, 15);
+    tc_fence_after();
+    for (int k = k0; k < k1; ++k) {
+      const int j = k - k0;
+      const bool have = (started >> j) & 1u;
+      float* prow = g.partial + (((int64_t)chunk * K + k) * g.Cin + (ci < g.Cin ? ci : 0)) * g.Cout;
+      const uint32_t taddr = tmem_base + j * g.Cout + ((uint32_t)(warp * 32) << 16);
+      for (int n = 0; n < g.Cout; n += 16) {
+        uint32_t v[16];
+        if (have) {
+          tmem_ld16(taddr + n, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0u;
+        }
+        if (ci < g.Cin) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(prow + n + 4 * q) =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t kSmemBudget = 225 * 1024;
+
+static inline size_t tail_bytes(int sa, int sb) {  // id ring + barriers + tmem slot + alignment slack
+  const int ni = 8 * kProdWarps;
+  return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 2) * 8 + 16 + 1024;
+}
+
+}  // namespace v2
+
+int debug_profile(long long* out16, int reset) {
+  if (out16) LG_CUDA_OK(cudaMemcpyFromSymbol(out16, v2::g_prof, sizeof(long long) * 16));
+  if (reset) {
+    long long z[16] = {0};
+    LG_CUDA_OK(cudaMemcpyToSymbol(v2::g_prof, z, sizeof(z)));
+  }
+  return LG_OK;
+}
+
+// host launcher: forward / dgrad
+int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void* B16, int N, int flip_k, int fmt,
+                    const float* out_scale, const float* bias, float* Y, cudaStream_t stream) {
+  using namespace v2;
+  int sm_count = 0;
+  int* err = nullptr;
+  int rc = tc_runtime(&sm_count, &err);
+  if (rc) return rc;
+  Gemm2Args g;
+  g.plan = *plan;
+  g.A = (const uint16_t*)A16;
+  g.Y = Y;
+  g.out_scale = out_scale;
+  g.bias = bias;
+  g.Ck = Ck;
+  g.N = N;
+  const int n_split = (N + 255) / 256;
+  g.n_blk = N / n_split;
+  if (g.n_blk % 16 != 0 || g.n_blk * n_split != N) {
+    set_error("lg_conv_gemm_tc: N=%d cannot be split into equal multiples of 16", N);
+    return LG_ERR_UNSUPPORTED;
+  }
+  g.flip = flip_k;
+  {
+    const char* e = getenv("LIDOG_DBG");
+    g.dbg = e ? atoi(e) : 0;
+  }
+  g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
+  g.n_tiles = plan->n_slots / LG_TILE_ROWS;
+  g.err = err;
+  const int n_chunks = Ck / 32;
+  g.n_panels = (n_chunks + 3) / 4;
+  while (n_chunks % g.n_panels != 0) ++g.n_panels;
+  g.pc = n_chunks / g.n_panels;
+  // tiles per super-tile: as many accumulators as TMEM holds (<= 8), but keep >= ~3 super-tiles per SM
+  int T = 512 / g.n_blk;
+  if (T > 8) T = 8;
+  while (T > 1 && ceil_div(g.n_tiles, T) * n_split < 3 * (int64_t)sm_count) --T;
+  g.T = T;
+  g.n_super = ceil_div(g.n_tiles, T);
+  size_t stageA, stageB;
+  for (;;) {
+    stageA = (size_t)g.pc * kSub, stageB = (size_t)g.pc * g.n_blk * kRowB;
+    g.sb = (3 * stageB <= 80 * 1024) ? 3 : 2;
+    g.sa = 12;
+    while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
+    if (g.sa >= kProdWarps || g.pc == 1) break;
+    // deeper ring with smaller panels (pc must divide the chunk count)
+    int pc = g.pc - 1;
+    while (n_chunks % pc != 0) --pc;
+    g.pc = pc;
+    g.n_panels = n_chunks / pc;
+  }
+  // Ring-phase rule: a producer warp revisits a stage only after the consumer freed it once, which the
+  // parity wait can tell only when consecutive units of one warp are < one ring wrap apart: np <= sa.
+  g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
+  const size_t smem = g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb);
+  if (smem > kSmemBudget) {
+    set_error("lg_conv_gemm_tc: shared memory %zu exceeds the budget (Ck=%d N=%d)", smem, Ck, N);
+    return LG_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmB;
+  memset(&tmB, 0, sizeof(tmB));
+  rc = tc_make_tmap(&tmB, B16, (int64_t)plan->kernel_volume * N, Ck, g.n_blk);
+  if (rc) return rc;
+  LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(g.n_super < sm_count ? g.n_super : sm_count), (unsigned)n_split);
+  k_gemm2<<<grid, kThreads, smem, stream>>>(g, tmB);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+static int wgrad2_shape(const lgConvPlan* plan, int Cin, int Cout, int* G, int* n_groups, int* tiles_per_chunk) {
+  const int K = plan->kernel_volume;
+  int gmax = 512 / Cout;
+  if (gmax > 8) gmax = 8;
+  if (gmax > K) gmax = K;
+  *n_groups = (K + gmax - 1) / gmax;
+  *G = (K + *n_groups - 1) / *n_groups;
+  const int m_blocks = (Cin + 127) / 128;
+  const int64_t n_tiles = plan->n_slots / LG_TILE_ROWS;
+  int64_t want = 592 / ((int64_t)*n_groups * m_blocks);
+  if (want < 1) want = 1;
+  int64_t chunks = n_tiles < want ? n_tiles : want;
+  if (chunks < 1) chunks = 1;
+  *tiles_per_chunk = (int)ceil_div(n_tiles > 0 ? n_tiles : 1, chunks);
+  return (int)ceil_div(n_tiles > 0 ? n_tiles : 1, *tiles_per_chunk);
+}
+
+size_t wgrad_tc2_workspace(const lgConvPlan* plan, int Cin, int Cout) {
+  int G, ng, tpc;
+  const int chunks = wgrad2_shape(plan, Cin, Cout, &G, &ng, &tpc);
+  return (size_t)chunks * plan->kernel_volume * Cin * Cout * sizeof(float) + 256;
+}
+
+int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const void* dY16, int Cout, int fmt,
+                     const float* out_scale, float* dW, void* workspace, cudaStream_t stream) {
+  using namespace v2;
+  int sm_count = 0;
+  int* err = nullptr;
+  int rc = tc_runtime(&sm_count, &err);
+  if (rc) return rc;
+  Wgrad2Args g;
+  g.plan = *plan;
+  g.X = (const uint16_t*)X16;
+  g.dY = (const uint16_t*)dY16;
+  g.partial = (float*)workspace;
+  g.Cin = Cin;
+  g.Cout = Cout;
+  g.m_blocks = (Cin + 127) / 128;
+  const int chunks = wgrad2_shape(plan, Cin, Cout, &g.G, &g.n_groups, &g.tiles_per_chunk);
+  g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
+  g.n_tiles = plan->n_slots / LG_TILE_ROWS;
+  g.err = err;
+  const size_t stageA = 4 * (size_t)kSub, stageB = (size_t)(Cout / 32) * kSub;
+  g.sb = 2;
+  g.sa = 5;
+  while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
+  g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
+  const size_t smem = g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb);
+  if (smem > kSmemBudget) {
+    set_error("lg_conv_wgrad_tc: shared memory %zu exceeds the budget (Cin=%d Cout=%d)", smem, Cin, Cout);
+    return LG_ERR_UNSUPPORTED;
+  }
+  LG_CUDA_OK(cudaFuncSetAttribute(k_wgrad2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(g.n_groups * g.m_blocks), (unsigned)chunks);
+  k_wgrad2<<<grid, kThreads, smem, stream>>>(g);
+  LG_LAUNCH_OK();
+  return launch_reduce_partials((const float*)workspace, chunks, (int64_t)plan->kernel_volume * Cin * Cout, out_scale,
+                                dW, stream);
+}
+
+}  // namespace lg
+
+// experiment hook (not part of the reference-facing ABI): per-role wait cycles of CTA 0, LIDOG_DBG & 8
+extern "C" int lg_debug_profile(long long* out16, int reset) { return lg::debug_profile(out16, reset); }

@@ -18,10 +18,12 @@ from .. import cabi
 from .sparse_tensor import SparseTensor
 
 # operand format of the tensor-core path: "fp16" (default; 2^-11 unit round-off meets the 1e-3 bar),
-# "bf16", or "off" (SIMT fp32 everywhere).  TC_GATHER: 0 = cp.async rows, 1 = TMA gather4.
+# "bf16", or "off" (SIMT fp32 everywhere).  TC_GATHER: 2 = super-tile pipeline with cp.async row gathers
+# arriving on mbarriers (default, csrc/conv_tc2.cu); 0 = first-generation cp.async; 1 = TMA tile::gather4
+# (kept for the record: measured 2.7x slower than cp.async on B200, profiles/).
 CONFIG = {
     "tc": os.environ.get("LIDOG_TC", "fp16"),
-    "gather": int(os.environ.get("LIDOG_TC_GATHER", "1")),
+    "gather": int(os.environ.get("LIDOG_TC_GATHER", "2")),
 }
 
 

@@ -46,7 +46,7 @@ def main():
     ap.add_argument("--fmt", default="fp16")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cases", default="all")
-    ap.add_argument("--gather", default="0,1")
+    ap.add_argument("--gather", default="0,2")
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
     args = ap.parse_args()
 
