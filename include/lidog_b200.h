@@ -105,6 +105,16 @@ int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_
                   int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int64_t n_slots, uint32_t* tile_mask,
                   void* stream);
 
+/* Same neighbour table with the rows REORDERED so that rows with the same neighbour pattern share a
+ * 128-row tile (kernel_size <= 3): slot s serves result row out_row[s] (-1 = padding) and gathers
+ * nbr[k][s].  The pair SET is identical to lg_kernel_map's; only the processing order differs (sort key:
+ * the row's offset bits, rarest offset most significant; stable, deterministic).  The convolution kernels
+ * then issue ~2.4x fewer (tile, offset) units on LiDAR scans.  Same reference contract as lg_kernel_map. */
+size_t lg_kernel_map_sorted_workspace(int64_t n_out, int32_t kernel_size);
+int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
+                         int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int32_t* out_row, int64_t n_slots,
+                         uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream);
+
 size_t lg_scan_workspace(int64_t n_items);
 
 /* ME-format pair lists from a neighbour table: pairs sorted by (k, out);

@@ -73,9 +73,12 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 struct TileMasks {
   uint32_t w[8];
 };
+// All mask helpers are called by fully active warps and broadcast lane 0's value, so everything derived
+// from them (unit sequence, stage counters, descriptors) is warp-uniform for ptxas.
 __device__ __forceinline__ void load_masks(TileMasks& tm, const lgConvPlan& p, int64_t tile0, int nt, int word) {
 #pragma unroll
-  for (int t = 0; t < 8; ++t) tm.w[t] = (t < nt) ? __ldg(p.tile_mask + (tile0 + t) * p.mask_words + word) : 0u;
+  for (int t = 0; t < 8; ++t)
+    tm.w[t] = (t < nt) ? bcast0(__ldg(p.tile_mask + (tile0 + t) * p.mask_words + word)) : 0u;
 }
 __device__ __forceinline__ uint32_t present_bits(const TileMasks& tm, int k) {
   uint32_t m = 0;
@@ -90,7 +93,7 @@ __device__ __forceinline__ uint32_t any_mask(const lgConvPlan& p, int64_t tile0,
     for (int i = 0; i < p.mask_words; ++i) w |= __ldg(p.tile_mask + (tile0 + t) * p.mask_words + i);
     m |= (w != 0 ? 1u : 0u) << t;
   }
-  return m;
+  return bcast0(m);
 }
 
 // Gather 128 rows x (PC * 32) channels of a row-major 16-bit matrix into `dst` (PC sub-tiles of 8 KB,
@@ -161,8 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   uint64_t* fullI = emptyB + g.sb;
   uint64_t* emptyI = fullI + ni;
   uint64_t* acc_full = emptyI + ni;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 1);
+  uint64_t* acc_empty = acc_full + 1;  // one per accumulator (tile slot of the super-tile)
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 8);
   const int n0 = blockIdx.y * g.n_blk;
   const int K = g.plan.kernel_volume;
   const bool prof = (g.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       mbar_init(&emptyI[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kEpiWarps * 32);
+    for (int t = 0; t < 8; ++t) mbar_init(&acc_empty[t], kEpiWarps * 32);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
@@ -193,30 +196,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kIdxWarp) {
-    // ===================================================================== id ring (one thread, runs ahead)
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t iphase = 0;
-      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
-        const int64_t tile0 = st * g.T;
-        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-        TileMasks tm;
-        for (int k = 0; k < K; ++k) {
-          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
-          const uint32_t m = present_bits(tm, k);
-          if (!m) continue;
-          for (int p = 0; p < g.n_panels; ++p) {
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-              const int t = __ffs(mm) - 1;
-              mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
+    // ===================================================================== id ring (runs ahead; one elected lane issues)
+    int slot = 0;
+    uint32_t iphase = 0;
+    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+      const int64_t tile0 = st * g.T;
+      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      TileMasks tm;
+      for (int k = 0; k < K; ++k) {
+        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        const uint32_t m = present_bits(tm, k);
+        if (!m) continue;
+        for (int p = 0; p < g.n_panels; ++p) {
+          for (uint32_t mm = m; mm; mm &= mm - 1) {
+            const int t = __ffs(mm) - 1;
+            mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
+            if (elect_one()) {
               mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
               bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
                             g.plan.nbr + (int64_t)k * g.plan.k_stride + (tile0 + t) * LG_TILE_ROWS, kIdxSlotBytes,
                             &fullI[slot]);
-              if (++slot == ni) {
-                slot = 0;
-                iphase ^= 1;
-              }
+            }
+            __syncwarp();
+            if (++slot == ni) {
+              slot = 0;
+              iphase ^= 1;
             }
           }
         }
@@ -270,21 +274,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     }
   } else if (warp == kBWarp) {
     // ===================================================================== B producer (weight panels, TMA)
-    if (lane == 0) {
-      int bs = 0;
-      uint32_t bphase = 0;
-      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
-        const int64_t tile0 = st * g.T;
-        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-        TileMasks tm;
-        for (int k = 0; k < K; ++k) {
-          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
-          if (!present_bits(tm, k)) continue;
-          const int wk = g.flip ? (K - 1 - k) : k;
-          for (int p = 0; p < g.n_panels; ++p) {
-            PROF_T0();
-            mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 2);
-            PROF_ADD(2);
+    int bs = 0;
+    uint32_t bphase = 0;
+    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+      const int64_t tile0 = st * g.T;
+      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      TileMasks tm;
+      for (int k = 0; k < K; ++k) {
+        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        if (!present_bits(tm, k)) continue;
+        const int wk = g.flip ? (K - 1 - k) : k;
+        for (int p = 0; p < g.n_panels; ++p) {
+          PROF_T0();
+          mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 2);
+          PROF_ADD(2);
+          if (elect_one()) {
             if (g.dbg & 1) {
               mbar_arrive(&fullB[bs]);
             } else {
@@ -293,85 +297,95 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
               for (int c = 0; c < g.pc; ++c)
                 tma_load_2d(dst + c * g.n_blk * kRowB, &tmB, (p * g.pc + c) * 32, wk * g.N + n0, &fullB[bs]);
             }
-            if (++bs == g.sb) {
-              bs = 0;
-              bphase ^= 1;
-            }
+          }
+          __syncwarp();
+          if (++bs == g.sb) {
+            bs = 0;
+            bphase ^= 1;
           }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer (one thread)
-    // The whole role runs in lane 0: descriptors are a constant high word plus (address >> 4), so a unit
-    // costs a barrier wait, two adds per MMA and a commit -- the tensor pipe, not this thread, sets the pace.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.umma_fmt, 0, 0, LG_TILE_ROWS, g.n_blk);
-      const uint64_t desc_hi = make_smem_desc(0, 16, 8 * kRowB, kLayoutSw64);
-      const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
-      const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
-      const uint32_t b_sub16 = (uint32_t)(g.n_blk * kRowB) >> 4;
-      const int pc = g.pc;
-      int stage = 0, bs = 0;
-      uint32_t phase = 0, bphase = 0, it = 0;
-      for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
-        const int64_t tile0 = st * g.T;
-        const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-        if (!any_mask(g.plan, tile0, nt)) continue;
-        PROF_T0();
-        mbar_wait(acc_empty, (it & 1) ^ 1, g.err, 3);
-        PROF_ADD(3);
-        ++it;
-        tc_fence_after();
-        uint32_t started = 0;
-        TileMasks tm;
-        for (int k = 0; k < K; ++k) {
-          if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
-          const uint32_t m = present_bits(tm, k);
-          if (!m) continue;
-          for (int p = 0; p < g.n_panels; ++p) {
-            mbar_wait(&fullB[bs], bphase, g.err, 4);
-            PROF_ADD(4);
-            const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-              const int t = __ffs(mm) - 1;
-              PROF_ADD(7);
-              mbar_wait(&fullA[stage], phase, g.err, 5);
-              PROF_ADD(5);
-              if (!(g.dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
-              tc_fence_after();
-              PROF_ADD(10);
-              const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
-              const uint32_t d_tmem = tmem_base + t * g.n_blk;
-              uint32_t acc = (started >> t) & 1u;
+    // ===================================================================== MMA issuer
+    // The loop runs warp-uniformly (every lane computes the same unit sequence; the masks are broadcast), and
+    // one elected lane issues the tcgen05 instructions: descriptors are a constant high word plus
+    // (address >> 4) held in uniform registers, so a unit costs two barrier waits, a proxy fence and 2*pc
+    // back-to-back UTCHMMAs.  Accumulators are handed back by the epilogue tile by tile (acc_empty[t]), so
+    // the first offsets of the next super-tile overlap the drain of the previous one.
+    const uint32_t idesc = make_idesc(g.umma_fmt, 0, 0, LG_TILE_ROWS, g.n_blk);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 8 * kRowB, kLayoutSw64);
+    const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
+    const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
+    const uint32_t b_sub16 = (uint32_t)(g.n_blk * kRowB) >> 4;
+    const int pc = g.pc;
+    int stage = 0, bs = 0;
+    uint32_t phase = 0, bphase = 0, it = 0;
+    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+      const int64_t tile0 = st * g.T;
+      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      if (!any_mask(g.plan, tile0, nt)) continue;
+      const uint32_t eparity = (it & 1) ^ 1;
+      ++it;
+      uint32_t started = 0;
+      TileMasks tm;
+      for (int k = 0; k < K; ++k) {
+        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        const uint32_t m = present_bits(tm, k);
+        if (!m) continue;
+        for (int p = 0; p < g.n_panels; ++p) {
+          PROF_T0();
+          mbar_wait(&fullB[bs], bphase, g.err, 4);
+          PROF_ADD(4);
+          const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
+          for (uint32_t mm = m; mm; mm &= mm - 1) {
+            const int t = __ffs(mm) - 1;
+            PROF_ADD(7);
+            if (!((started >> t) & 1u)) mbar_wait(&acc_empty[t], eparity, g.err, 3);
+            PROF_ADD(3);
+            mbar_wait(&fullA[stage], phase, g.err, 5);
+            PROF_ADD(5);
+            if (!(g.dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
+            tc_fence_after();
+            PROF_ADD(10);
+            const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
+            const uint32_t d_tmem = tmem_base + t * g.n_blk;
+            const uint32_t acc0 = (started >> t) & 1u;
+            if (elect_one()) {
+              if (!(g.dbg & 4)) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                if (c < pc && !(g.dbg & 4)) {
-                  umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, acc);
-                  umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
-                  acc = 1u;
+                for (int c = 0; c < 4; ++c) {
+                  if (c < pc) {
+                    umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, c == 0 ? acc0 : 1u);
+                    umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
+                  }
                 }
               }
-              PROF_ADD(6);
               umma_commit(&emptyA[stage]);
-              PROF_ADD(11);
-              started |= 1u << t;
-              if (++stage == g.sa) {
-                stage = 0;
-                phase ^= 1;
-              }
             }
-            umma_commit(&emptyB[bs]);
-            if (++bs == g.sb) {
-              bs = 0;
-              bphase ^= 1;
+            __syncwarp();
+            PROF_ADD(6);
+            started |= 1u << t;
+            if (++stage == g.sa) {
+              stage = 0;
+              phase ^= 1;
             }
           }
+          if (elect_one()) umma_commit(&emptyB[bs]);
+          __syncwarp();
+          if (++bs == g.sb) {
+            bs = 0;
+            bphase ^= 1;
+          }
         }
-        umma_commit(acc_full);
       }
+      // accumulators this super-tile never touched: consume their hand-off too, so that no acc_empty
+      // barrier is ever more than one phase ahead of this warp
+      for (int t = 0; t < g.T; ++t)
+        if (!((started >> t) & 1u)) mbar_wait(&acc_empty[t], eparity, g.err, 3);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================================================================== epilogue (warps 0..3)
     const float scale = g.out_scale ? g.out_scale[0] : 1.f;
@@ -387,45 +401,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
         tc_fence_after();
       }
       if (warp == 0) PROF_ADD(8);
-      for (int t = 0; t < nt; ++t) {
-        const int64_t s = (tile0 + t) * LG_TILE_ROWS + warp * 32 + lane;
-        int64_t row = g.plan.out_row ? (int64_t)g.plan.out_row[s] : s;
-        const bool row_ok = row >= 0 && row < g.plan.n_out;
-        float* yrow = g.Y + (row_ok ? row : 0) * g.N + n0;
-        if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
-          if (row_ok)
-            for (int n = 0; n < g.n_blk; n += 4) {
-              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
-              *reinterpret_cast<float4*>(yrow + n) = o;
-            }
-          continue;
-        }
-        const uint32_t taddr = tmem_base + t * g.n_blk + ((uint32_t)(warp * 32) << 16);
-        for (int n = 0; n < g.n_blk; n += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + n, v);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 o;
-              o.x = __uint_as_float(v[4 * q + 0]) * scale;
-              o.y = __uint_as_float(v[4 * q + 1]) * scale;
-              o.z = __uint_as_float(v[4 * q + 2]) * scale;
-              o.w = __uint_as_float(v[4 * q + 3]) * scale;
-              if (g.bias) {
-                const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
-                o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+      for (int t = 0; t < g.T; ++t) {
+        if (t < nt) {
+          const int64_t s = (tile0 + t) * LG_TILE_ROWS + warp * 32 + lane;
+          int64_t row = g.plan.out_row ? (int64_t)g.plan.out_row[s] : s;
+          const bool row_ok = row >= 0 && row < g.plan.n_out;
+          float* yrow = g.Y + (row_ok ? row : 0) * g.N + n0;
+          if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
+            if (row_ok)
+              for (int n = 0; n < g.n_blk; n += 4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
+                *reinterpret_cast<float4*>(yrow + n) = o;
               }
-              *reinterpret_cast<float4*>(yrow + n + 4 * q) = o;
+          } else {
+            const uint32_t taddr = tmem_base + t * g.n_blk + ((uint32_t)(warp * 32) << 16);
+            for (int n = 0; n < g.n_blk; n += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + n, v);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float4 o;
+                  o.x = __uint_as_float(v[4 * q + 0]) * scale;
+                  o.y = __uint_as_float(v[4 * q + 1]) * scale;
+                  o.z = __uint_as_float(v[4 * q + 2]) * scale;
+                  o.w = __uint_as_float(v[4 * q + 3]) * scale;
+                  if (g.bias) {
+                    const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
+                    o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+                  }
+                  *reinterpret_cast<float4*>(yrow + n + 4 * q) = o;
+                }
+              }
             }
           }
         }
-      }
-      if (am) {
-        tc_fence_before();
-        mbar_arrive(acc_empty);
+        if (am) {  // hand accumulator t back (tcgen05.ld of it have completed: wait::ld above)
+          tc_fence_before();
+          mbar_arrive(&acc_empty[t]);
+        }
       }
       if (warp == 0) PROF_ADD(9);
     }
@@ -508,25 +524,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     const uint32_t* mw = g.plan.tile_mask + tile * g.plan.mask_words;
     const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;
     const uint64_t bits = (uint64_t)__ldg(mw + w0) | (w1 != w0 ? (uint64_t)__ldg(mw + w1) << 32 : 0ull);
-    return (uint32_t)(bits >> (k0 & 31)) & ((1u << (k1 - k0)) - 1u);
+    return bcast0((uint32_t)(bits >> (k0 & 31)) & ((1u << (k1 - k0)) - 1u));
   };
 
   if (warp == kIdxWarp) {
-    // ---------------------------------------------------------------- id ring (one thread, runs ahead)
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t iphase = 0;
-      for (int64_t tile = t0; tile < t1; ++tile) {
-        for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
-          const int k = k0 + __ffs(mm) - 1;
-          mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 16);
+    // ---------------------------------------------------------------- id ring (runs ahead; one elected lane issues)
+    int slot = 0;
+    uint32_t iphase = 0;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+      for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
+        const int k = k0 + __ffs(mm) - 1;
+        mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 16);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
           bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
                         g.plan.nbr + (int64_t)k * g.plan.k_stride + tile * LG_TILE_ROWS, kIdxSlotBytes, &fullI[slot]);
-          if (++slot == ni) {
-            slot = 0;
-            iphase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++slot == ni) {
+          slot = 0;
+          iphase ^= 1;
         }
       }
     }
@@ -587,44 +604,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.umma_fmt, 1, 1, 128, g.Cout);
-      // MN-major SWIZZLE_64B: LBO = pitch between 32-channel sub-blocks, SBO = 8 rows * 64 B
-      const uint64_t desc_hi = make_smem_desc(0, kSub, 8 * kRowB, kLayoutSw64);
-      const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
-      const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
-      int stage = 0, bs = 0;
-      uint32_t phase = 0, bphase = 0, started = 0;
-      for (int64_t tile = t0; tile < t1; ++tile) {
-        const uint32_t m = group_mask(tile);
-        if (!m) continue;
-        mbar_wait(&fullB[bs], bphase, g.err, 13);
+    // warp-uniform loop, one elected lane issues (see k_gemm2)
+    const uint32_t idesc = make_idesc(g.umma_fmt, 1, 1, 128, g.Cout);
+    // MN-major SWIZZLE_64B: LBO = pitch between 32-channel sub-blocks, SBO = 8 rows * 64 B
+    const uint64_t desc_hi = make_smem_desc(0, kSub, 8 * kRowB, kLayoutSw64);
+    const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
+    const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
+    int stage = 0, bs = 0;
+    uint32_t phase = 0, bphase = 0, started = 0;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+      const uint32_t m = group_mask(tile);
+      if (!m) continue;
+      mbar_wait(&fullB[bs], bphase, g.err, 13);
+      const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
+      for (uint32_t mm = m; mm; mm &= mm - 1) {
+        const int j = __ffs(mm) - 1;
+        mbar_wait(&fullA[stage], phase, g.err, 14);
         fence_proxy_async();
-        const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
-        for (uint32_t mm = m; mm; mm &= mm - 1) {
-          const int j = __ffs(mm) - 1;
-          mbar_wait(&fullA[stage], phase, g.err, 14);
-          fence_proxy_async();
-          tc_fence_after();
-          const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
-          const uint32_t d_tmem = tmem_base + j * g.Cout;
-          umma_f16(d_tmem, da0, db0, idesc, (started >> j) & 1u);
+        tc_fence_after();
+        const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
+        const uint32_t d_tmem = tmem_base + j * g.Cout;
+        const uint32_t acc0 = (started >> j) & 1u;
+        if (elect_one()) {
+          umma_f16(d_tmem, da0, db0, idesc, acc0);
 #pragma unroll
           for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
             umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
           umma_commit(&emptyA[stage]);
-          started |= 1u << j;
-          if (++stage == g.sa) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&emptyB[bs]);
-        if (++bs == g.sb) {
-          bs = 0;
-          bphase ^= 1;
+        __syncwarp();
+        started |= 1u << j;
+        if (++stage == g.sa) {
+          stage = 0;
+          phase ^= 1;
         }
       }
+      if (elect_one()) umma_commit(&emptyB[bs]);
+      __syncwarp();
+      if (++bs == g.sb) {
+        bs = 0;
+        bphase ^= 1;
+      }
+    }
+    if (elect_one()) {
       if (started)
         umma_commit(done);
       else
@@ -671,7 +693,7 @@ constexpr size_t kSmemBudget = 225 * 1024;
 
 static inline size_t tail_bytes(int sa, int sb) {  // id ring + barriers + tmem slot + alignment slack
   const int ni = 8 * kProdWarps;
-  return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 2) * 8 + 16 + 1024;
+  return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 10) * 8 + 16 + 1024;
 }
 
 }  // namespace v2

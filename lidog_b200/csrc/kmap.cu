@@ -4,6 +4,8 @@
 // (conventions: SURVEY.md Appendix C.7).  A warp owns 32 consecutive output voxels and walks the
 // kernel offsets together, so nbr[k][o..o+31] is written coalesced and the tile mask falls out of a
 // ballot; the table (16 B slots, load factor <= 0.5) stays L2-resident.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -14,7 +16,8 @@ constexpr int kMaxMaskWords = 4;  // K <= 128 (5^3 = 125)
 __global__ void __launch_bounds__(LG_TILE_ROWS)
     k_neighbors(const HashSlot* __restrict__ table, unsigned long long mask, const int4* __restrict__ out_coords,
                 int64_t n_out, int ksize, int scale, int K, int mask_words, int32_t* __restrict__ nbr,
-                int64_t n_slots, uint32_t* __restrict__ tile_mask) {
+                int64_t n_slots, uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ row_mask,
+                unsigned int* __restrict__ k_count) {
   __shared__ uint32_t s_mask[kMaxMaskWords];
   if (threadIdx.x < kMaxMaskWords) s_mask[threadIdx.x] = 0;
   __syncthreads();
@@ -23,6 +26,7 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
   int4 c = valid ? out_coords[o] : make_int4(0, 0, 0, 0);
   const int base = (ksize & 1) ? -(ksize / 2) : 0;
   uint32_t wmask[kMaxMaskWords] = {0, 0, 0, 0};
+  uint32_t rmask = 0;  // this row's offsets (sorted plans only, K <= 32)
   int k = 0;
   for (int iz = 0; iz < ksize; ++iz)
     for (int iy = 0; iy < ksize; ++iy)
@@ -33,8 +37,14 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
           if (coord_in_range(c.x, x, y, z)) r = hash_lookup(table, mask, pack_key(c.x, x, y, z));
         }
         nbr[(int64_t)k * n_slots + o] = r;
-        if (__ballot_sync(0xffffffffu, r >= 0)) wmask[k >> 5] |= 1u << (k & 31);
+        const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
+        if (bal) wmask[k >> 5] |= 1u << (k & 31);
+        if (row_mask) {
+          rmask |= (r >= 0 ? 1u : 0u) << (k & 31);
+          if (bal && (threadIdx.x & 31) == 0) atomicAdd(&k_count[k], (unsigned)__popc(bal));
+        }
       }
+  if (row_mask) row_mask[o] = rmask;
   if ((threadIdx.x & 31) == 0) {
     for (int w = 0; w < mask_words; ++w)
       if (wmask[w]) atomicOr(&s_mask[w], wmask[w]);
@@ -119,6 +129,56 @@ __global__ void k_up2_layout(const int* k_start, int64_t n, int* k_slot_base, ui
   *slots_used = base;
 }
 
+// ---- mask-sorted plans: rows with the same neighbour pattern share tiles
+// Sort key of a row = its offset bits, the RAREST offset (smallest pair count, ties by k) most
+// significant: rows that own an unusual neighbour end up together, so far fewer (tile, offset)
+// units carry mostly-empty rows (measured on kitti-shaped scans: 0.29 -> 0.69 of the gathered rows real).
+__global__ void k_sort_keys(const uint32_t* __restrict__ row_mask, const unsigned int* __restrict__ k_count, int K,
+                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  __shared__ int s_pos[32];
+  if (threadIdx.x < 32) {
+    const int k = threadIdx.x;
+    int rank = 0;  // number of offsets rarer than k
+    if (k < K) {
+      const unsigned ck = k_count[k];
+      for (int j = 0; j < K; ++j) {
+        const unsigned cj = k_count[j];
+        rank += (cj < ck || (cj == ck && j < k)) ? 1 : 0;
+      }
+    }
+    s_pos[k] = K - 1 - rank;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t m = row_mask[i];
+  uint32_t key = 0;
+  for (int k = 0; k < K; ++k) key |= ((m >> k) & 1u) << s_pos[k];
+  keys[i] = key;
+  vals[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(LG_TILE_ROWS)
+    k_permute_plan(const int32_t* __restrict__ nbr_nat, const int32_t* __restrict__ perm, int64_t n_out, int K,
+                   int64_t n_slots, int32_t* __restrict__ nbr, int32_t* __restrict__ out_row,
+                   uint32_t* __restrict__ tile_mask) {
+  __shared__ uint32_t s_mask;
+  if (threadIdx.x == 0) s_mask = 0;
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.x * LG_TILE_ROWS + threadIdx.x;
+  const int r = (s < n_out) ? perm[s] : -1;
+  out_row[s] = r;
+  uint32_t wmask = 0;
+  for (int k = 0; k < K; ++k) {
+    const int v = (r >= 0) ? nbr_nat[(int64_t)k * n_slots + r] : -1;
+    nbr[(int64_t)k * n_slots + s] = v;
+    if (__ballot_sync(0xffffffffu, v >= 0)) wmask |= 1u << k;
+  }
+  if ((threadIdx.x & 31) == 0 && wmask) atomicOr(&s_mask, wmask);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_mask[blockIdx.x] = s_mask;
+}
+
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -140,7 +200,80 @@ extern "C" int lg_kernel_map(const void* table_in, int64_t capacity_in, const in
   const int words = (K + 31) / 32;
   k_neighbors<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, (cudaStream_t)stream>>>(
       (const HashSlot*)table_in, (unsigned long long)(capacity_in - 1), (const int4*)out_coords4, n_out, kernel_size,
-      offset_scale, K, words, nbr, n_slots, tile_mask);
+      offset_scale, K, words, nbr, n_slots, tile_mask, nullptr, nullptr);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+namespace {
+struct SortedWs {
+  int32_t* nbr_nat;
+  uint32_t *row_mask, *keys_in, *keys_out, *nat_tile_mask;
+  int32_t *vals_in, *vals_out;
+  unsigned int* k_count;
+  void* cub_tmp;
+  size_t cub_bytes, total;
+};
+SortedWs carve_sorted(void* base, int64_t n_out, int K) {
+  const int64_t n_slots = round_up(n_out > 0 ? n_out : 1, LG_TILE_ROWS);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? (char*)base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return (void*)p;
+  };
+  SortedWs w;
+  w.nbr_nat = (int32_t*)take(sizeof(int32_t) * (size_t)K * n_slots);
+  w.row_mask = (uint32_t*)take(4 * (size_t)n_slots);
+  w.keys_in = (uint32_t*)take(4 * (size_t)n_slots);
+  w.keys_out = (uint32_t*)take(4 * (size_t)n_slots);
+  w.vals_in = (int32_t*)take(4 * (size_t)n_slots);
+  w.vals_out = (int32_t*)take(4 * (size_t)n_slots);
+  w.nat_tile_mask = (uint32_t*)take(4 * (size_t)(n_slots / LG_TILE_ROWS));
+  w.k_count = (unsigned int*)take(4 * 32);
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_slots, 0, K);
+  w.cub_tmp = take(w.cub_bytes);
+  w.total = off + 256;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t lg_kernel_map_sorted_workspace(int64_t n_out, int32_t kernel_size) {
+  if (kernel_size < 1 || kernel_size > 3) return 0;
+  return carve_sorted(nullptr, n_out, kernel_size * kernel_size * kernel_size).total;
+}
+
+extern "C" int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, const int32_t* out_coords4,
+                                    int64_t n_out, int32_t kernel_size, int32_t offset_scale, int32_t* nbr,
+                                    int32_t* out_row, int64_t n_slots, uint32_t* tile_mask, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LG_CHECK_ARG(kernel_size >= 1 && kernel_size <= 3, "lg_kernel_map_sorted: kernel_size %d not in [1,3]", kernel_size);
+  LG_CHECK_ARG(n_out >= 0 && n_slots == round_up(n_out, LG_TILE_ROWS),
+               "lg_kernel_map_sorted: n_slots must be round_up(n_out,128)");
+  LG_CHECK_ARG(capacity_in >= 1024 && (capacity_in & (capacity_in - 1)) == 0, "lg_kernel_map_sorted: bad capacity");
+  LG_CHECK_ARG(n_out < ((int64_t)1 << 31), "lg_kernel_map_sorted: too many rows");
+  if (n_out == 0) return LG_OK;
+  LG_CHECK_ARG(table_in && out_coords4 && nbr && out_row && tile_mask && workspace, "lg_kernel_map_sorted: null pointer");
+  LG_CHECK_ARG(workspace_bytes >= lg_kernel_map_sorted_workspace(n_out, kernel_size),
+               "lg_kernel_map_sorted: workspace too small");
+  const int K = kernel_size * kernel_size * kernel_size;
+  SortedWs w = carve_sorted(workspace, n_out, K);
+  LG_CUDA_OK(cudaMemsetAsync(w.k_count, 0, 4 * 32, stream));
+  k_neighbors<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, stream>>>(
+      (const HashSlot*)table_in, (unsigned long long)(capacity_in - 1), (const int4*)out_coords4, n_out, kernel_size,
+      offset_scale, K, 1, w.nbr_nat, n_slots, w.nat_tile_mask, w.row_mask, w.k_count);
+  LG_LAUNCH_OK();
+  k_sort_keys<<<(unsigned)ceil_div(n_out, 256), 256, 0, stream>>>(w.row_mask, w.k_count, K, n_out, w.keys_in,
+                                                                  w.vals_in);
+  LG_LAUNCH_OK();
+  size_t cub_bytes = w.cub_bytes;
+  LG_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, (const uint32_t*)w.keys_in, w.keys_out,
+                                             (const int32_t*)w.vals_in, w.vals_out, (int)n_out, 0, K, stream));
+  k_permute_plan<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, stream>>>(w.nbr_nat, w.vals_out, n_out, K,
+                                                                                   n_slots, nbr, out_row, tile_mask);
   LG_LAUNCH_OK();
   return LG_OK;
 }

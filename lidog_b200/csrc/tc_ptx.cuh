@@ -40,6 +40,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must not hang the GPU box.  On timeout the error word is set and the
 // kernel traps (the launch fails with an error instead of spinning forever).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
   for (uint32_t it = 0; it < 40000000u; ++it) {
     if (mbar_try_wait(bar, parity)) return;
   }
@@ -47,6 +48,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   __threadfence_system();
   __trap();
 }
+
+// One lane of a fully active warp.  The single-thread roles (MMA issue, TMA issue) run their loops
+// warp-uniformly and elect a lane only for the instruction itself: descriptors then live in uniform
+// registers and UTCHMMA / UTMALDG issue back to back, instead of the R2UR + ELECT/BRA waterfall ptxas
+// emits around every such instruction inside a divergent `if (lane == 0)` region.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

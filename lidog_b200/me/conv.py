@@ -24,6 +24,8 @@ from .sparse_tensor import SparseTensor
 CONFIG = {
     "tc": os.environ.get("LIDOG_TC", "fp16"),
     "gather": int(os.environ.get("LIDOG_TC_GATHER", "2")),
+    # mask-sorted gather plans (lg_kernel_map_sorted) for the 3x3x3 and stride-2 layers; 0 = natural row order
+    "sorted": int(os.environ.get("LIDOG_SORTED_PLANS", "1")),
 }
 
 
@@ -198,17 +200,21 @@ class MinkowskiConvolutionBase(nn.Module):
                 raise NotImplementedError("transposed convolution is implemented for kernel 2 / stride 2")
             if ts_out not in cm.levels:
                 raise RuntimeError("transposed convolution needs the finer coordinate map created by the encoder")
-            up, down = cm.plan("up", ts_in, ts_out, 2), cm.plan("down", ts_out, ts_in, 2)
+            up, down = cm.plan("up", ts_in, ts_out, 2), cm.plan(self._kind("down"), ts_out, ts_in, 2)
             return ts_out, (up, down, up, 0)
         ts_out = ts_in * s
         if s == 2:
-            down, up = cm.plan("down", ts_in, ts_out, 2), cm.plan("up", ts_out, ts_in, 2)
+            down, up = cm.plan(self._kind("down"), ts_in, ts_out, 2), cm.plan("up", ts_out, ts_in, 2)
             return ts_out, (down, up, down, 0)
         if k == 1:
             p = cm.plan("identity", ts_in, ts_in, 1)
             return ts_out, (p, p, p, 0)
-        p = cm.plan("same", ts_in, ts_in, k)
+        p = cm.plan(self._kind("same") if k == 3 else "same", ts_in, ts_in, k)
         return ts_out, (p, p, p, 1)
+
+    @staticmethod
+    def _kind(kind):
+        return kind + "_sorted" if CONFIG["sorted"] else kind
 
     def forward(self, input: SparseTensor) -> SparseTensor:
         assert isinstance(input, SparseTensor)

@@ -130,6 +130,23 @@ class CoordinateManager:
                                    scale, cabi.ptr(nbr), n_slots, cabi.ptr(mask), cabi.stream()), "lg_kernel_map")
         return GatherPlan(nbr, n_slots, None, mask, K, n_slots, n_out, lvl_in.n)
 
+    def _sorted_plan(self, lvl_in: Level, lvl_out: Level, ksize: int, scale: int) -> GatherPlan:
+        """Mask-sorted processing order (lg_kernel_map_sorted): same pair set, rows with the same neighbour
+        pattern share a tile.  This is what the convolution layers run on."""
+        L = cabi.lib()
+        K = ksize ** 3
+        n_out = lvl_out.n
+        n_slots = _round_up(n_out, cabi.TILE)
+        nbr = torch.empty((K, max(n_slots, 1)), dtype=torch.int32, device=self.device)
+        out_row = torch.empty(max(n_slots, 1), dtype=torch.int32, device=self.device)
+        mask = torch.empty((max(n_slots // cabi.TILE, 1), 1), dtype=torch.int32, device=self.device)
+        ws_bytes = L.lg_kernel_map_sorted_workspace(n_out, ksize)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        cabi.check(L.lg_kernel_map_sorted(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out,
+                                          ksize, scale, cabi.ptr(nbr), cabi.ptr(out_row), n_slots, cabi.ptr(mask),
+                                          cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_kernel_map_sorted")
+        return GatherPlan(nbr, n_slots, out_row, mask, K, n_slots, n_out, lvl_in.n)
+
     def _plan_same(self, ts_in, ts_out, ksize):
         assert ts_in == ts_out and ksize % 2 == 1
         lvl = self.level(ts_in)
@@ -138,6 +155,15 @@ class CoordinateManager:
     def _plan_down(self, ts_in, ts_out, ksize):
         assert ts_out == 2 * ts_in and ksize == 2
         return self._neighbor_plan(self.level(ts_in), self.level(ts_out), 2, ts_in)
+
+    def _plan_same_sorted(self, ts_in, ts_out, ksize):
+        assert ts_in == ts_out and ksize == 3
+        lvl = self.level(ts_in)
+        return self._sorted_plan(lvl, lvl, ksize, ts_in)
+
+    def _plan_down_sorted(self, ts_in, ts_out, ksize):
+        assert ts_out == 2 * ts_in and ksize == 2
+        return self._sorted_plan(self.level(ts_in), self.level(ts_out), 2, ts_in)
 
     def _plan_up(self, ts_in, ts_out, ksize):
         """coarse (ts_in) -> fine (ts_out): fine rows grouped by child index, one k per tile."""
@@ -169,8 +195,8 @@ class CoordinateManager:
     # ------------------------------------------------------------------ ME-format kernel maps (tests / interop)
     def kernel_map_pairs(self, plan: GatherPlan):
         """(in_rows, out_rows, k_offsets) sorted by (k, out) -- MinkowskiEngine's kernel-map format."""
-        if plan.k_stride == 0:
-            raise ValueError("pair lists are defined for neighbour-table plans only")
+        if plan.k_stride == 0 or plan.out_row is not None:
+            raise ValueError("pair lists are defined for natural-order neighbour-table plans only")
         L = cabi.lib()
         total = plan.K * plan.n_slots
         in_rows = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)

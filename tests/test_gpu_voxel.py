@@ -124,6 +124,33 @@ def test_kernel_map_pairs_match_oracle(cuda, ksize, ts):
             assert bool((mask[t, k // 32] >> (k % 32)) & 1) == bool(has)
 
 
+@pytest.mark.parametrize("kind,ksize,ts", [("same", 3, 1), ("same", 3, 2), ("down", 2, 1), ("down", 2, 2)])
+def test_sorted_plan_is_a_row_permutation_of_the_natural_plan(cuda, kind, ksize, ts):
+    """lg_kernel_map_sorted: identical pair set, out_row a permutation, tile masks consistent, deterministic."""
+    rng = np.random.default_rng(6)
+    coords = random_voxels(rng, 20000)
+    cm = _manager(coords, cuda)
+    ts_out = ts if kind == "same" else 2 * ts
+    nat = cm.plan(kind, ts, ts_out, ksize)
+    srt = cm.plan(kind + "_sorted", ts, ts_out, ksize)
+    n_out = nat.n_out
+    assert srt.n_out == n_out and srt.n_slots == nat.n_slots and srt.K == nat.K
+    orow = srt.out_row.cpu().numpy()
+    assert np.array_equal(np.sort(orow[:n_out]), np.arange(n_out)) and np.all(orow[n_out:] == -1)
+    nn, sn = nat.nbr.cpu().numpy(), srt.nbr.cpu().numpy()
+    assert np.array_equal(sn[:, :n_out], nn[:, orow[:n_out]])  # slot s gathers what row out_row[s] gathers
+    assert np.all(sn[:, n_out:] == -1)
+    mask = srt.tile_mask.cpu().numpy().view(np.uint32).reshape(-1)
+    for t in range(sn.shape[1] // 128):
+        for k in range(sn.shape[0]):
+            assert bool((mask[t] >> k) & 1) == bool((sn[k, t * 128:(t + 1) * 128] >= 0).any())
+    # fewer (tile, offset) units than the natural order, and the same plan when built again
+    units = lambda m: int(sum(bin(int(v)).count("1") for v in m.reshape(-1)))
+    assert units(mask) <= units(nat.tile_mask.cpu().numpy().view(np.uint32))
+    again = cm._sorted_plan(cm.level(ts), cm.level(ts_out), ksize, ts)
+    assert torch.equal(again.out_row, srt.out_row) and torch.equal(again.nbr, srt.nbr)
+
+
 def test_stride2_plans_match_oracle(cuda):
     rng = np.random.default_rng(5)
     coords = random_voxels(rng, 20000)

@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--cases", default="all")
     ap.add_argument("--gather", default="0,2")
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
+    ap.add_argument("--sorted", default="0,1", help="gather-plan row order: 0 natural, 1 mask-sorted")
     args = ap.parse_args()
 
     from lidog_b200 import cabi
@@ -67,46 +68,50 @@ def main():
     dt16 = torch.float16 if args.fmt == "fp16" else torch.bfloat16
     L = cabi.lib()
     only = args.only.split(",")
-    for kind, ts, ks, cin, cout in (CASES_ALL if args.cases == "all" else CASES_TOP):
-        cls = ME.MinkowskiConvolutionTranspose if kind == "up" else ME.MinkowskiConvolution
-        layer = cls(cin, cout, kernel_size=ks, stride=2 if kind in ("down", "up") else 1, dimension=3)
-        ts_out, (p_fwd, p_dgrad, p_wgrad, flip) = layer._plans(cm, ts)
-        K = ks ** 3
-        pairs = p_fwd.count_pairs()
-        mask = p_fwd.tile_mask.view(torch.int32)
-        units = int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in mask.flatten().tolist()))
-        units_d = int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in p_dgrad.tile_mask.view(torch.int32).flatten().tolist()))
-        x16 = torch.randn(p_fwd.n_in, cin, device=dev).relu_().to(dt16)
-        dy16 = (torch.randn(p_fwd.n_out, cout, device=dev)).to(dt16)
-        w16 = torch.randn(K, cin, cout, device=dev).to(dt16)
-        w16t = w16.transpose(1, 2).contiguous()
-        y = torch.empty(p_fwd.n_out, cout, device=dev)
-        dx = torch.empty(p_fwd.n_in, cin, device=dev)
-        dw = torch.empty(K, cin, cout, device=dev)
-        ws_bytes = L.lg_conv_wgrad_tc_workspace(p_wgrad.c, cin, cout)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        for gather in [int(g) for g in args.gather.split(",")]:
-            res = {}
-            if "fwd" in only:
-                res["fwd"] = (timed(lambda: cabi.check(L.lg_conv_gemm_tc(
-                    p_fwd.c, cabi.ptr(x16), cin, cabi.ptr(w16t), cout, 0, fmt, None, None, cabi.ptr(y), gather,
-                    cabi.stream())), args.reps), units, cin, cout)
-            if "dgrad" in only:
-                res["dgrad"] = (timed(lambda: cabi.check(L.lg_conv_gemm_tc(
-                    p_dgrad.c, cabi.ptr(dy16), cout, cabi.ptr(w16), cin, flip, fmt, None, None, cabi.ptr(dx), gather,
-                    cabi.stream())), args.reps), units_d, cout, cin)
-            if "wgrad" in only:
-                res["wgrad"] = (timed(lambda: cabi.check(L.lg_conv_wgrad_tc(
-                    p_wgrad.c, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt, None, cabi.ptr(dw), gather, cabi.ptr(ws),
-                    ws_bytes, cabi.stream())), args.reps), units, cin, cout)
-            for name, (ms, u, a, b) in res.items():
-                alg = 2.0 * pairs * cin * cout / (ms * 1e-3) / 1e12
-                dense = 2.0 * u * 128 * cin * cout / (ms * 1e-3) / 1e12
-                cyc = ms * 1e-3 * clock_mhz * 1e6 * sm_count / max(u, 1)
-                print(json.dumps(dict(case=f"{kind} ts{ts} k{ks} {cin}->{cout}", op=name, gather=gather, ms=round(ms, 4),
-                                      n_out=p_fwd.n_out, pairs=pairs, units=u, density=round(pairs / max(u * 128, 1), 3),
-                                      alg_tflops=round(alg, 1), dense_tflops=round(dense, 1),
-                                      sm_cycles_per_unit=round(cyc))), flush=True)
+    for srt in [int(v) for v in args.sorted.split(",")]:
+      meconv.CONFIG["sorted"] = srt
+      for kind, ts, ks, cin, cout in (CASES_ALL if args.cases == "all" else CASES_TOP):
+          if srt == 1 and kind in ("up", "identity") and "0" in args.sorted.split(","):
+              continue  # these plans have no sorted variant
+          cls = ME.MinkowskiConvolutionTranspose if kind == "up" else ME.MinkowskiConvolution
+          layer = cls(cin, cout, kernel_size=ks, stride=2 if kind in ("down", "up") else 1, dimension=3)
+          ts_out, (p_fwd, p_dgrad, p_wgrad, flip) = layer._plans(cm, ts)
+          K = ks ** 3
+          pairs = p_fwd.count_pairs()
+          mask = p_fwd.tile_mask.view(torch.int32)
+          units = int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in mask.flatten().tolist()))
+          units_d = int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in p_dgrad.tile_mask.view(torch.int32).flatten().tolist()))
+          x16 = torch.randn(p_fwd.n_in, cin, device=dev).relu_().to(dt16)
+          dy16 = (torch.randn(p_fwd.n_out, cout, device=dev)).to(dt16)
+          w16 = torch.randn(K, cin, cout, device=dev).to(dt16)
+          w16t = w16.transpose(1, 2).contiguous()
+          y = torch.empty(p_fwd.n_out, cout, device=dev)
+          dx = torch.empty(p_fwd.n_in, cin, device=dev)
+          dw = torch.empty(K, cin, cout, device=dev)
+          ws_bytes = L.lg_conv_wgrad_tc_workspace(p_wgrad.c, cin, cout)
+          ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+          for gather in [int(g) for g in args.gather.split(",")]:
+              res = {}
+              if "fwd" in only:
+                  res["fwd"] = (timed(lambda: cabi.check(L.lg_conv_gemm_tc(
+                      p_fwd.c, cabi.ptr(x16), cin, cabi.ptr(w16t), cout, 0, fmt, None, None, cabi.ptr(y), gather,
+                      cabi.stream())), args.reps), units, cin, cout)
+              if "dgrad" in only:
+                  res["dgrad"] = (timed(lambda: cabi.check(L.lg_conv_gemm_tc(
+                      p_dgrad.c, cabi.ptr(dy16), cout, cabi.ptr(w16), cin, flip, fmt, None, None, cabi.ptr(dx), gather,
+                      cabi.stream())), args.reps), units_d, cout, cin)
+              if "wgrad" in only:
+                  res["wgrad"] = (timed(lambda: cabi.check(L.lg_conv_wgrad_tc(
+                      p_wgrad.c, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt, None, cabi.ptr(dw), gather, cabi.ptr(ws),
+                      ws_bytes, cabi.stream())), args.reps), units, cin, cout)
+              for name, (ms, u, a, b) in res.items():
+                  alg = 2.0 * pairs * cin * cout / (ms * 1e-3) / 1e12
+                  dense = 2.0 * u * 128 * cin * cout / (ms * 1e-3) / 1e12
+                  cyc = ms * 1e-3 * clock_mhz * 1e6 * sm_count / max(u, 1)
+                  print(json.dumps(dict(case=f"{kind} ts{ts} k{ks} {cin}->{cout}", op=name, gather=gather, sorted=srt, ms=round(ms, 4),
+                                        n_out=p_fwd.n_out, pairs=pairs, units=u, density=round(pairs / max(u * 128, 1), 3),
+                                        alg_tflops=round(alg, 1), dense_tflops=round(dense, 1),
+                                        sm_cycles_per_unit=round(cyc))), flush=True)
 
 
 if __name__ == "__main__":
