@@ -199,6 +199,9 @@ def run_ours(args):
     cfg = synth.SHAPES[args.shape]
     torch.manual_seed(1234)
     net = M.MinkUNet34BEV(1, args.classes, mapping_bound_2d=cfg["bound"]).to(dev)
+    from lidog_b200.lidog import bev as lbev
+    if lbev.CONFIG["channels_last"]:  # 4-D (2D-head) parameters only; the logical shapes do not change
+        net.encoders2d.to(memory_format=torch.channels_last)
     if world > 1:  # train_lidog.py:227-231
         net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
         ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])

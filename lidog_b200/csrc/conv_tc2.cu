@@ -49,6 +49,10 @@ constexpr int kProdWarps = 4;        // warps 6..9
 constexpr int kIdxWarp = kProdWarp0 + kProdWarps;  // warp 10: row-id ring (bulk copies of 512 B id rows)
 constexpr int kThreads = (kIdxWarp + 1) * 32;
 constexpr int kIdxSlotBytes = LG_TILE_ROWS * 4;
+constexpr int kSchedSlots = 4;                                   // super-tile hand-out ring
+constexpr int kSchedConsumers = kEpiWarps + 2 + kProdWarps;      // warps that read every ring entry
+constexpr int kStgPitch = 36;                                    // floats per staged row (32 + 4: conflict-free v4)
+constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;        // epilogue transposition buffers
 
 __device__ __forceinline__ uint32_t sw64(uint32_t r, uint32_t j) { return r * kRowB + ((j ^ ((r >> 1) & 3u)) << 4); }
 
@@ -67,6 +71,26 @@ __device__ __forceinline__ int lds32(uint32_t saddr) {
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Dynamic super-tile schedule.  The id warp draws super-tiles from a global counter (largest index first:
+// with mask-sorted plans the expensive tiles sit at the end, so the tail of the launch is made of cheap
+// ones) and publishes them through a 4-entry shared-memory ring; every other warp reads each entry once.
+struct SchedCursor {
+  int slot;
+  uint32_t phase;
+};
+__device__ __forceinline__ int64_t sched_next(SchedCursor& c, uint64_t* fullS, uint64_t* emptyS, const int* ring,
+                                              int lane, int* err) {
+  mbar_wait(&fullS[c.slot], c.phase, err, 20);
+  const int st = (int)bcast0((uint32_t) * (const volatile int*)(ring + c.slot));
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&emptyS[c.slot]);
+  if (++c.slot == kSchedSlots) {
+    c.slot = 0;
+    c.phase ^= 1;
+  }
+  return st;
 }
 
 // tile-mask words of the (<= 8) tiles of a super-tile, kept in registers; reloaded every 32 offsets
@@ -144,8 +168,11 @@ struct Gemm2Args {
   int Ck, N, n_blk, flip, umma_fmt;
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
+  int sets;                         // accumulator sets in TMEM (sets * T * n_blk <= 512): 2 = the epilogue of one
+                                    // super-tile overlaps the MMAs of the next
   int64_t n_tiles, n_super;
   int* err;
+  int* sched;  // [0..3] next super-tile per blockIdx.y, [4] finished CTAs (self-resetting)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const __grid_constant__ CUtensorMap tmB) {
@@ -157,19 +184,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   uint8_t* smB = smem + (size_t)g.sa * stageA;
   uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
   const int ni = 8 * g.np;
-  uint64_t* fullA = (uint64_t*)(smI + (size_t)ni * kIdxSlotBytes);
+  float* smStg = (float*)(smI + (size_t)ni * kIdxSlotBytes);  // epilogue transposition buffers
+  uint64_t* fullA = (uint64_t*)((uint8_t*)smStg + kStgBytes);
   uint64_t* emptyA = fullA + g.sa;
   uint64_t* fullB = emptyA + g.sa;
   uint64_t* emptyB = fullB + g.sb;
   uint64_t* fullI = emptyB + g.sb;
   uint64_t* emptyI = fullI + ni;
   uint64_t* acc_full = emptyI + ni;
-  uint64_t* acc_empty = acc_full + 1;  // one per accumulator (tile slot of the super-tile)
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 8);
+  uint64_t* acc_empty = acc_full + 2;  // one per accumulator: [set * T + tile slot]
+  uint64_t* fullS = acc_empty + 8;
+  uint64_t* emptyS = fullS + kSchedSlots;
+  uint32_t* tmem_slot = (uint32_t*)(emptyS + kSchedSlots);
+  int* sched_ring = (int*)(tmem_slot + 2);
+  SchedCursor sc{0, 0};
   const int n0 = blockIdx.y * g.n_blk;
   const int K = g.plan.kernel_volume;
   const bool prof = (g.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
-  long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pacc[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long cta_t0 = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.sa; ++s) {
@@ -184,8 +217,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       mbar_init(&fullI[s], 1);
       mbar_init(&emptyI[s], 1);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     for (int t = 0; t < 8; ++t) mbar_init(&acc_empty[t], kEpiWarps * 32);
+    for (int t = 0; t < kSchedSlots; ++t) {
+      mbar_init(&fullS[t], 1);
+      mbar_init(&emptyS[t], kSchedConsumers);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
@@ -199,7 +237,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== id ring (runs ahead; one elected lane issues)
     int slot = 0;
     uint32_t iphase = 0;
-    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+    for (;;) {
+      mbar_wait(&emptyS[sc.slot], sc.phase ^ 1, g.err, 21);
+      int drawn = 0;
+      if (lane == 0) drawn = atomicAdd(g.sched + blockIdx.y, 1);
+      drawn = (int)bcast0((uint32_t)drawn);
+      const int64_t st = drawn < g.n_super ? g.n_super - 1 - drawn : -1;
+      if (lane == 0) {
+        sched_ring[sc.slot] = (int)st;
+        mbar_arrive(&fullS[sc.slot]);
+      }
+      __syncwarp();
+      if (++sc.slot == kSchedSlots) {
+        sc.slot = 0;
+        sc.phase ^= 1;
+      }
+      if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks tm;
@@ -231,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     const int pw = warp - kProdWarp0;
     int stage = 0, turn = 0, slot = 0;
     uint32_t phase = 0, iphase = 0;
-    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+    for (;;) {
+      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks tm;
@@ -276,7 +331,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== B producer (weight panels, TMA)
     int bs = 0;
     uint32_t bphase = 0;
-    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+    for (;;) {
+      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks tm;
@@ -321,11 +378,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     const int pc = g.pc;
     int stage = 0, bs = 0;
     uint32_t phase = 0, bphase = 0, it = 0;
-    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+    for (;;) {
+      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       if (!any_mask(g.plan, tile0, nt)) continue;
-      const uint32_t eparity = (it & 1) ^ 1;
+      const int set = (g.sets == 2) ? (int)(it & 1) : 0;
+      const uint32_t eparity = (((g.sets == 2) ? (it >> 1) : it) & 1) ^ 1;
+      const int a0 = set * g.T;  // first accumulator of this set
       ++it;
       uint32_t started = 0;
       TileMasks tm;
@@ -341,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
           for (uint32_t mm = m; mm; mm &= mm - 1) {
             const int t = __ffs(mm) - 1;
             PROF_ADD(7);
-            if (!((started >> t) & 1u)) mbar_wait(&acc_empty[t], eparity, g.err, 3);
+            if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
             PROF_ADD(3);
             mbar_wait(&fullA[stage], phase, g.err, 5);
             PROF_ADD(5);
@@ -349,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             tc_fence_after();
             PROF_ADD(10);
             const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
-            const uint32_t d_tmem = tmem_base + t * g.n_blk;
+            const uint32_t d_tmem = tmem_base + (a0 + t) * g.n_blk;
             const uint32_t acc0 = (started >> t) & 1u;
             if (elect_one()) {
               if (!(g.dbg & 4)) {
@@ -366,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             __syncwarp();
             PROF_ADD(6);
             started |= 1u << t;
+            pacc[13] += 1;  // units
             if (++stage == g.sa) {
               stage = 0;
               phase ^= 1;
@@ -382,21 +444,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       // accumulators this super-tile never touched: consume their hand-off too, so that no acc_empty
       // barrier is ever more than one phase ahead of this warp
       for (int t = 0; t < g.T; ++t)
-        if (!((started >> t) & 1u)) mbar_wait(&acc_empty[t], eparity, g.err, 3);
-      if (elect_one()) umma_commit(acc_full);
+        if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
+      if (elect_one()) umma_commit(&acc_full[set]);
       __syncwarp();
+      pacc[14] += 1;  // super-tiles
     }
+    pacc[12] = clock64() - cta_t0;  // lifetime of the MMA role of this CTA
   } else {
     // ===================================================================== epilogue (warps 0..3)
     const float scale = g.out_scale ? g.out_scale[0] : 1.f;
     uint32_t it = 0;
-    for (int64_t st = blockIdx.x; st < g.n_super; st += gridDim.x) {
+    for (;;) {
+      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       const uint32_t am = any_mask(g.plan, tile0, nt);
       PROF_T0();
+      int a0 = 0;
       if (am) {
-        mbar_wait(acc_full, it & 1, g.err, 6);
+        const int set = (g.sets == 2) ? (int)(it & 1) : 0;
+        a0 = set * g.T;
+        mbar_wait(&acc_full[set], ((g.sets == 2) ? (it >> 1) : it) & 1, g.err, 6);
         ++it;
         tc_fence_after();
       }
@@ -415,8 +484,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
                 *reinterpret_cast<float4*>(yrow + n) = o;
               }
           } else {
-            const uint32_t taddr = tmem_base + t * g.n_blk + ((uint32_t)(warp * 32) << 16);
-            for (int n = 0; n < g.n_blk; n += 16) {
+            // TMEM lane = tile row, so a thread holds 32 consecutive columns of ONE row; storing them directly
+            // makes every warp store touch 32 different lines (measured: the epilogue was store-bound).  The
+            // 32x32 block goes through shared memory instead and leaves as 4 rows x 128 contiguous bytes per
+            // warp instruction.
+            const uint32_t taddr = tmem_base + (a0 + t) * g.n_blk + ((uint32_t)(warp * 32) << 16);
+            float* stg = smStg + warp * 32 * kStgPitch;
+            int srow[8];  // result rows this lane stores: tile rows (lane >> 3) + 4 j
+#pragma unroll
+            for (int j = 0; j < 8; ++j) srow[j] = __shfl_sync(0xffffffffu, row_ok ? (int)row : -1, (lane >> 3) + 4 * j);
+            int n = 0;
+            for (; n + 32 <= g.n_blk; n += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + n, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 o;
+                o.x = __uint_as_float(v[4 * q + 0]) * scale;
+                o.y = __uint_as_float(v[4 * q + 1]) * scale;
+                o.z = __uint_as_float(v[4 * q + 2]) * scale;
+                o.w = __uint_as_float(v[4 * q + 3]) * scale;
+                if (g.bias) {
+                  const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
+                  o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+                }
+                *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * q) = o;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
+                if (srow[j] >= 0)
+                  *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
+              }
+              __syncwarp();
+            }
+            for (; n < g.n_blk; n += 16) {  // 16-column remainder (N % 32 == 16): direct stores
               uint32_t v[16];
               tmem_ld16(taddr + n, v);
               tmem_ld_wait();
@@ -440,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
         }
         if (am) {  // hand accumulator t back (tcgen05.ld of it have completed: wait::ld above)
           tc_fence_before();
-          mbar_arrive(&acc_empty[t]);
+          mbar_arrive(&acc_empty[a0 + t]);
         }
       }
       if (warp == 0) PROF_ADD(9);
@@ -449,11 +553,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   if (warp == kProdWarp0) PROF_FLUSH(0, 1);
   if (warp == kBWarp) PROF_FLUSH(2, 2);
   if (warp == kMmaWarp) PROF_FLUSH(3, 7);
-  if (warp == kMmaWarp) PROF_FLUSH(10, 11);
+  if (warp == kMmaWarp) PROF_FLUSH(10, 14);
   if (warp == 0) PROF_FLUSH(8, 9);
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) {  // the last CTA to finish rewinds the counters for the launch that reuses this slot
+    __threadfence();
+    const int done = atomicAdd(g.sched + 4, 1);
+    if (done == (int)(gridDim.x * gridDim.y) - 1) {
+      for (int y = 0; y < 5; ++y) g.sched[y] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ wgrad
@@ -494,8 +606,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
   uint64_t* emptyI = fullI + ni;
   uint64_t* done = emptyI + ni;
   uint32_t* tmem_slot = (uint32_t*)(done + 1);
-  const int64_t t0 = (int64_t)chunk * g.tiles_per_chunk;
-  const int64_t t1 = min(t0 + g.tiles_per_chunk, g.n_tiles);
+  // chunk c owns tiles c, c + chunks, c + 2 chunks, ...: with mask-sorted plans neighbouring tiles have the
+  // same offsets, so interleaving gives every CTA of an offset group the same amount of work
+  const int64_t t0 = chunk, t1 = g.n_tiles, tstep = gridDim.y;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.sa; ++s) {
@@ -531,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     // ---------------------------------------------------------------- id ring (runs ahead; one elected lane issues)
     int slot = 0;
     uint32_t iphase = 0;
-    for (int64_t tile = t0; tile < t1; ++tile) {
+    for (int64_t tile = t0; tile < t1; tile += tstep) {
       for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
         const int k = k0 + __ffs(mm) - 1;
         mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 16);
@@ -552,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     const int pw = warp - kProdWarp0;
     int stage = 0, turn = 0, slot = 0;
     uint32_t phase = 0, iphase = 0;
-    for (int64_t tile = t0; tile < t1; ++tile) {
+    for (int64_t tile = t0; tile < t1; tile += tstep) {
       for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
         if (turn == pw) {
           int rows[16];
@@ -583,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     int bs = 0;
     uint32_t bphase = 0;
     const int lim = (int)g.plan.n_out;
-    for (int64_t tile = t0; tile < t1; ++tile) {
+    for (int64_t tile = t0; tile < t1; tile += tstep) {
       if (!group_mask(tile)) continue;
       int rows[16];
 #pragma unroll
@@ -612,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
     int stage = 0, bs = 0;
     uint32_t phase = 0, bphase = 0, started = 0;
-    for (int64_t tile = t0; tile < t1; ++tile) {
+    for (int64_t tile = t0; tile < t1; tile += tstep) {
       const uint32_t m = group_mask(tile);
       if (!m) continue;
       mbar_wait(&fullB[bs], bphase, g.err, 13);
@@ -656,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
   } else {
     // ---------------------------------------------------------------- epilogue: lane = input channel
     uint32_t started = 0;
-    for (int64_t tile = t0; tile < t1; ++tile) started |= group_mask(tile);
+    for (int64_t tile = t0; tile < t1; tile += tstep) started |= group_mask(tile);
     const int ci = m0 + warp * 32 + lane;
     mbar_wait(done, 0, g.err, 15);
     tc_fence_after();
@@ -691,12 +804,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
 
 constexpr size_t kSmemBudget = 225 * 1024;
 
-static inline size_t tail_bytes(int sa, int sb) {  // id ring + barriers + tmem slot + alignment slack
+static inline size_t wgrad_tail_bytes(int sa, int sb) {  // id ring + barriers + tmem slot + alignment slack
   const int ni = 8 * kProdWarps;
-  return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 10) * 8 + 16 + 1024;
+  return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 2) * 8 + 16 + 1024;
+}
+static inline size_t tail_bytes(int sa, int sb) {  // + epilogue staging + schedule ring
+  const int ni = 8 * kProdWarps;
+  return (size_t)ni * kIdxSlotBytes + kStgBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 11 + 2 * kSchedSlots) * 8 + 16 +
+         4 * kSchedSlots + 1024;
 }
 
 }  // namespace v2
+
+// Schedule counters: 64 slots of 8 ints, handed out round-robin so launches in flight on different
+// streams never share one; every kernel leaves its slot zeroed.
+static int* g_sched_pool = nullptr;
+static unsigned g_sched_seq = 0;
+static int sched_slot(int** out) {
+  if (!g_sched_pool) {
+    LG_CUDA_OK(cudaMalloc(&g_sched_pool, 64 * 8 * sizeof(int)));
+    LG_CUDA_OK(cudaMemset(g_sched_pool, 0, 64 * 8 * sizeof(int)));
+  }
+  *out = g_sched_pool + 8 * (g_sched_seq++ % 64);
+  return LG_OK;
+}
 
 int debug_profile(long long* out16, int reset) {
   if (out16) LG_CUDA_OK(cudaMemcpyFromSymbol(out16, v2::g_prof, sizeof(long long) * 16));
@@ -737,6 +868,12 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
   g.n_tiles = plan->n_slots / LG_TILE_ROWS;
   g.err = err;
+  rc = sched_slot(&g.sched);
+  if (rc) return rc;
+  if (n_split > 4) {
+    set_error("lg_conv_gemm_tc: N=%d needs more than 4 column blocks", N);
+    return LG_ERR_UNSUPPORTED;
+  }
   const int n_chunks = Ck / 32;
   g.n_panels = (n_chunks + 3) / 4;
   while (n_chunks % g.n_panels != 0) ++g.n_panels;
@@ -745,6 +882,17 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   int T = 512 / g.n_blk;
   if (T > 8) T = 8;
   while (T > 1 && ceil_div(g.n_tiles, T) * n_split < 3 * (int64_t)sm_count) --T;
+  // two accumulator sets when that still leaves T >= 1 (LIDOG_ACC_SETS=1 forces the single-set schedule)
+  g.sets = 1;
+  {
+    const char* e = getenv("LIDOG_ACC_SETS");
+    const int want = e ? atoi(e) : 2;
+    if (want == 2 && 2 * g.n_blk <= 512) {
+      g.sets = 2;
+      const int tmax = 512 / (2 * g.n_blk) < 4 ? 512 / (2 * g.n_blk) : 4;  // 2 * T accumulator barriers <= 8
+      if (T > tmax) T = tmax;
+    }
+  }
   g.T = T;
   g.n_super = ceil_div(g.n_tiles, T);
   size_t stageA, stageB;
@@ -824,9 +972,9 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   const size_t stageA = 4 * (size_t)kSub, stageB = (size_t)(Cout / 32) * kSub;
   g.sb = 2;
   g.sa = 5;
-  while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
+  while (g.sa > 2 && g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
-  const size_t smem = g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb);
+  const size_t smem = g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb);
   if (smem > kSmemBudget) {
     set_error("lg_conv_wgrad_tc: shared memory %zu exceeds the budget (Cin=%d Cout=%d)", smem, Cin, Cout);
     return LG_ERR_UNSUPPORTED;

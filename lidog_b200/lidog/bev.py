@@ -7,6 +7,7 @@ the per-sample Python loop and the dense 2000 x 2000 x C tensor.
 """
 from __future__ import annotations
 
+import os
 import types
 
 import torch
@@ -14,6 +15,10 @@ import torch
 from .. import cabi
 
 POLICIES = {"last": cabi.BEV_LAST, "max": cabi.BEV_MAX}
+
+# Memory format of the projected image handed to the dense 2D head (logical shape stays (B, C, h, w)):
+# channels_last lets cuDNN's tensor-op convolutions run without their NCHW<->NHWC staging copies.
+CONFIG = {"channels_last": int(os.environ.get("LIDOG_BEV_CHANNELS_LAST", "1"))}
 
 
 def image_size(bound: float, voxel_size: float) -> int:
@@ -61,6 +66,13 @@ def bev_project(coords, feats, batch_size, bound=50.0, voxel_size=0.05, pool=(5,
 
 def sparse2super(x, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last", batch_size=None):
     """x: SparseTensor (any tensor stride; coordinates in stride-1 voxel units) -> [B, C, h, w]."""
+    out = _sparse2super(x, bound, voxel_size, pool, policy, batch_size)
+    if CONFIG["channels_last"]:
+        out = out.contiguous(memory_format=torch.channels_last)
+    return out
+
+
+def _sparse2super(x, bound, voxel_size, pool, policy, batch_size):
     cm = x.coordinate_manager
     if batch_size is None:
         batch_size = getattr(cm, "batch_size", None)
