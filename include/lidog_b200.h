@@ -174,23 +174,66 @@ int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const
                      int32_t fmt, const float* out_scale, float* dW, int32_t gather_mode, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ fused batch norm (+ ReLU, residual, operand cast)
+ *
+ * ME.MinkowskiBatchNorm / MinkowskiSyncBatchNorm are torch BatchNorm1d on the N x C feature matrix, chained with
+ * ME.MinkowskiReLU and BasicBlock's `out += residual` at utils/models/minkunet_bev.py:308-368 (SyncBN conversion:
+ * train_lidog.py:228).  A layer is two HBM passes each way here; the sums between the passes are what SyncBN
+ * exchanges (the caller all-reduces `sums` and `count`).  C % 4 == 0, C <= 1024.  Deterministic.
+ *   stats float[4C] = [mean, invstd, scale = gamma*invstd, shift = beta - mean*scale] */
+size_t lg_bn_workspace(int64_t n, int32_t C);
+/* sums double[2C] = [sum x, sum x^2] of this rank's n rows. */
+int lg_bn_stats(const float* x, int64_t n, int32_t C, double* sums, void* workspace, size_t workspace_bytes,
+                void* stream);
+/* count = rows over all ranks (read from the device double *count_dev when that is non-NULL: the all-reduced
+ * count of SyncBN never visits the host); gamma/beta/running_* / num_batches_tracked (int64) nullable; running_var
+ * gets the unbiased variance, momentum as torch (new = (1-m)*old + m*batch). */
+int lg_bn_finalize(const double* sums, double count, const double* count_dev, int32_t C, const float* gamma,
+                   const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                   float* stats_out, void* stream);
+/* y = act(x*scale + shift [+ x2*scale2 + shift2] [+ res]), act = ReLU when relu != 0; y16 (nullable) receives the
+ * 16-bit copy (fmt) the next tensor-core convolution gathers. */
+int lg_bn_apply(const float* x, const float* stats, const float* x2, const float* stats2, const float* res,
+                int32_t relu, int64_t n, int32_t C, float* y, void* y16, int32_t fmt, void* stream);
+/* g = dy * [y > 0] (relu) or dy.  sums double[3C] = [sum g, sum g*(x-mean), sum g*(x2-mean2)],
+ * maxes float[3C] = [max|g|, max|x-mean|, max|x2-mean2|] per channel. */
+int lg_bn_bwd_stats(const float* dy, const float* y, const float* x, const float* stats, const float* x2,
+                    const float* stats2, int32_t relu, int64_t n, int32_t C, double* sums, float* maxes,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* branch 0 (x) or 1 (x2): coef float[3C] = [a, b, c], dx = a*g + b*(x-mean) + c; dgamma/dbeta (nullable) from
+ * sums_local (this rank), coefficients from sums_global (all ranks; = sums_local without SyncBN);
+ * scale_out float[3] = {2^k with bound*2^k in [2^11, 2^12), 2^-k, bound >= max|dx|}. */
+int lg_bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* maxes, double count,
+                       const double* count_dev, int32_t C, int32_t branch, const float* gamma, const float* stats, float* coef, float* dgamma,
+                       float* dbeta, float* scale_out, void* stream);
+int lg_bn_bwd_gscale(const float* maxes, int32_t C, float* scale_out, void* stream);
+/* dx (+ scaled 16-bit copy), optionally dx2 for the second BN branch and dres = g for a plain residual. */
+int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, const float* stats, const float* coef,
+                    const float* x2, const float* stats2, const float* coef2, int32_t relu, int64_t n, int32_t C,
+                    float* dx, void* dx16, const float* scale, float* dx2, void* dx2_16, const float* scale2,
+                    float* dres, void* dres16, const float* scale_r, int32_t fmt, void* stream);
+
 /* ------------------------------------------------------------------ BEV projection */
 
 size_t lg_bev_workspace(int64_t n, int32_t batch_size, int32_t H, int32_t W);
 
 /* Fused point-to-BEV projection: pixel scatter + raw (H,W,C)->(C,H,W) re-view + MaxPool2d(pk,ps,pp),
  * never materialising the dense tensor.  Replaces MinkUNetBaseBEV.sparse2super + filter_bounds
- * (utils/models/minkunet_bev.py:158-230).  out: float [batch, C, h, w], h = (H + 2pp - pk)/ps + 1.
+ * (utils/models/minkunet_bev.py:158-230).  out: float [batch, C, h, w], h = (H + 2pp - pk)/ps + 1, stored
+ * NCHW (layout 0) or NHWC / channels_last (layout 1: the same logical tensor, the memory order cuDNN's
+ * tensor-op convolutions of the dense 2D head consume without staging copies).
  * workspace keeps the pixel map for lg_bev_backward. */
 int lg_bev_forward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size, float bound,
                    float voxel_size, int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy,
-                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+                   int32_t layout, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (autograd of index_put_ + max_pool2d at minkunet_bev.py:217-221).
  * grad_feats [n, C] is fully written. */
 int lg_bev_backward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size,
-                    int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy, const float* grad_out,
-                    float* grad_feats, const void* workspace, size_t workspace_bytes, void* stream);
+                    int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy, int32_t layout,
+                    const float* grad_out, float* grad_feats, const void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 #ifdef __cplusplus
 }

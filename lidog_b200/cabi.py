@@ -54,11 +54,20 @@ SIGNATURES = {
     "lg_conv_gemm_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "lg_conv_wgrad_tc_workspace": (_sz, [_PP, _i32, _i32]),
     "lg_conv_wgrad_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "lg_bn_workspace": (_sz, [_i64, _i32]),
+    "lg_bn_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "lg_bn_finalize": (C.c_int, [_vp, C.c_double, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "lg_bn_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp]),
+    "lg_bn_bwd_stats": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "lg_bn_bwd_finalize": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lg_bn_bwd_gscale": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "lg_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _i32, _vp]),
     "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32]),
-    "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
-                                 _sz, _vp]),
-    "lg_bev_backward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz,
-                                  _vp]),
+    "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
+                                 _vp, _sz, _vp]),
+    "lg_bev_backward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
+                                  _sz, _vp]),
 }
 
 
@@ -69,6 +78,8 @@ KERNELS_PER_CALL = {
     "lg_kernel_map_up2": 9, "lg_conv_gemm_simt": 1, "lg_conv_wgrad_simt": 2, "lg_cast_rows": 1,
     "lg_absmax_scale": 2, "lg_prep_weights": 1, "lg_conv_gemm_tc": 1, "lg_conv_wgrad_tc": 2,
     "lg_bev_forward": 2, "lg_bev_backward": 3,
+    "lg_bn_stats": 2, "lg_bn_finalize": 1, "lg_bn_apply": 1, "lg_bn_bwd_stats": 2, "lg_bn_bwd_finalize": 1,
+    "lg_bn_bwd_gscale": 1, "lg_bn_bwd_apply": 1,
 }
 COUNTS: dict = {}
 

@@ -86,110 +86,227 @@ __device__ __forceinline__ int cell_argrow(int head, int ch, int C, int policy, 
   return arg;
 }
 
-struct RowGeom {
-  int b, cp, i;        // sample, scrambled channel, output row
-  int h_lo, rows;      // first valid scrambled row of the window, number of valid rows
-  int64_t m_lo;        // flat offset (within the sample's H*W*C buffer) of scrambled row h_lo
-  int64_t cells;       // rows * W
+// ---------------------------------------------------------------------------------------------
+// Tiled pooling.  A CTA owns the output tile (b, 32 scrambled channels c', kIB rows i, kJC columns j).
+// Per (c', h') the cells of its windows are one contiguous run of <= (kJC-1)*ps+pk floats of the
+// never-materialised dense buffer, i.e. a handful of consecutive PIXELS, and only ~2 % of the pixels
+// hold a voxel.  Phase 1 looks those pixels up once (pixel -> row heads in shared memory, plus one
+// "row has a voxel" bit per (c', h')).  Phase 2 evaluates every window in the reference's scan order:
+// windows whose rows are all empty cost one shared-memory read, empty cells are zeros, occupied cells
+// read their feature value (L1/L2 hits: neighbouring windows share pixels).  Results are staged in
+// shared memory and leave coalesced in NCHW or NHWC (channels_last, what cuDNN's tensor-op
+// convolutions consume).  No atomics in the forward; every output is written exactly once.
+constexpr int kCG = 32;   // scrambled channels per CTA
+constexpr int kIB = 8;    // output rows per CTA
+constexpr int kJC = 32;   // output columns per CTA
+constexpr int kPitch = kCG + 1;
+
+struct TileGeom {
+  int b, c0, i0, j0;  // sample, first scrambled channel, first output row / column
+  int ncg, nib, njc;  // valid extents of the tile
+  int h_lo, h_hi, w_lo, w_hi;  // cell region (clipped to the image), hi exclusive
 };
 
-__device__ __forceinline__ RowGeom row_geom(int C, int H, int W, int h_out, int pk, int ps, int pp) {
-  RowGeom g;
+__device__ __forceinline__ TileGeom tile_geom(int C, int H, int W, int h_out, int w_out, int pk, int ps, int pp) {
+  TileGeom g;
+  const int n_jc = (w_out + kJC - 1) / kJC, n_ib = (h_out + kIB - 1) / kIB, n_cg = (C + kCG - 1) / kCG;
   int idx = blockIdx.x;
-  g.i = idx % h_out;
-  idx /= h_out;
-  g.cp = idx % C;
-  g.b = idx / C;
-  int h0 = g.i * ps - pp;
-  g.h_lo = max(h0, 0);
-  int h_hi = min(h0 + pk, H);
-  g.rows = h_hi - g.h_lo;
-  g.m_lo = ((int64_t)g.cp * H + g.h_lo) * W;
-  g.cells = (int64_t)g.rows * W;
+  g.j0 = (idx % n_jc) * kJC;
+  idx /= n_jc;
+  g.i0 = (idx % n_ib) * kIB;
+  idx /= n_ib;
+  g.c0 = (idx % n_cg) * kCG;
+  g.b = idx / n_cg;
+  g.ncg = min(kCG, C - g.c0);
+  g.nib = min(kIB, h_out - g.i0);
+  g.njc = min(kJC, w_out - g.j0);
+  g.h_lo = max(g.i0 * ps - pp, 0);
+  g.h_hi = min((g.i0 + g.nib - 1) * ps - pp + pk, H);
+  g.w_lo = max(g.j0 * ps - pp, 0);
+  g.w_hi = min((g.j0 + g.njc - 1) * ps - pp + pk, W);
   return g;
 }
 
-// fills sm[0..cells) with the scrambled rows; returns false (uniformly) when the pixel run is empty
-__device__ __forceinline__ bool load_rows(const RowGeom& g, int C, int H, int W, int policy,
-                                          const float* __restrict__ feats, const int* __restrict__ next,
-                                          const int* __restrict__ pixmap, float* sm) {
+struct TileSmem {
+  float* out;         // [kIB][kJC][kPitch] staged results (forward) / gradients (backward)
+  int* heads;         // [pairs][max_pix] pixel -> row head (or -1)
+  int* plo;           // [pairs] first pixel of the run
+  uint32_t* rowmask;  // [kCG] bit (h - h_lo): scrambled row h of channel c' holds a voxel
+};
+__device__ __forceinline__ TileSmem carve_tile(unsigned char* base, int pairs_cap, int max_pix) {
+  TileSmem t;
+  t.out = reinterpret_cast<float*>(base);
+  t.heads = reinterpret_cast<int*>(t.out + kIB * kJC * kPitch);
+  t.plo = t.heads + pairs_cap * max_pix;
+  t.rowmask = reinterpret_cast<uint32_t*>(t.plo + pairs_cap);
+  return t;
+}
+
+// Phase 1.  Returns false (uniformly) when no pixel of the tile is occupied.
+__device__ __forceinline__ bool tile_lookup(const TileGeom& g, const TileSmem& t, int C, int H, int W, int max_pix,
+                                            const int* __restrict__ pixmap) {
+  const int nrows = g.h_hi - g.h_lo;
   const int* pm = pixmap + (int64_t)g.b * H * W;
-  const int64_t p_lo = g.m_lo / C, p_hi = (g.m_lo + g.cells - 1) / C;
   int any = 0;
-  for (int64_t p = p_lo + threadIdx.x; p <= p_hi; p += blockDim.x) any |= (__ldg(pm + p) >= 0);
-  if (!__syncthreads_or(any)) return false;
-  for (int64_t e = threadIdx.x; e < g.cells; e += blockDim.x) {
-    const int64_t m = g.m_lo + e;
-    const int64_t p = m / C;
-    const int ch = (int)(m - p * C);
-    sm[e] = cell_value(__ldg(pm + p), ch, C, policy, feats, next);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int cl = warp; cl < g.ncg; cl += nwarps) {  // lane = scrambled row (nrows <= 32, host-checked)
+    const int hr = lane;
+    int row_any = 0;
+    if (hr < nrows) {
+      const int q = cl * nrows + hr;
+      const int m_lo = ((g.c0 + cl) * H + g.h_lo + hr) * W + g.w_lo, m_hi = m_lo + (g.w_hi - g.w_lo);
+      const int p_lo = m_lo / C, p_hi = (m_hi - 1) / C;
+      t.plo[q] = p_lo;
+      for (int d = 0; d < max_pix; ++d) {
+        const int head = (p_lo + d <= p_hi) ? __ldg(pm + p_lo + d) : -1;
+        t.heads[q * max_pix + d] = head;
+        row_any |= (head >= 0);
+      }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, row_any);
+    if (lane == 0) t.rowmask[cl] = bits;
+    any |= (bits != 0);
   }
-  __syncthreads();
-  return true;
+  return __syncthreads_or(any) != 0;
+}
+
+// Scan of one window in the reference's order (rows, then columns; strict > keeps the first maximum).
+// Returns the pooled value; *arg_m = flat dense index of the winning cell, *arg_row = its voxel row
+// (-1 when an empty cell wins).  WANT_ARG = false skips the bookkeeping.
+template <bool WANT_ARG>
+__device__ __forceinline__ float window_scan(const TileGeom& g, const TileSmem& t, int cl, int i, int j, int C, int H,
+                                             int W, int pk, int ps, int pp, int max_pix, int policy,
+                                             const float* __restrict__ feats, const int* __restrict__ next,
+                                             int* arg_row, int* arg_ch) {
+  const int nrows = g.h_hi - g.h_lo;
+  const int h0 = i * ps - pp, w0 = j * ps - pp;
+  const int ha = max(h0, 0), hb = min(h0 + pk, H), wa = max(w0, 0), wb = min(w0 + pk, W);
+  const uint32_t rbits = (t.rowmask[cl] >> (ha - g.h_lo)) & ((1u << (hb - ha)) - 1u);
+  if (WANT_ARG) *arg_row = -1;
+  if (!rbits) return 0.f;  // every cell is an empty zero; the first one wins
+  float best = -INFINITY;
+  for (int h = ha; h < hb; ++h) {
+    if (!((rbits >> (h - ha)) & 1u)) {  // an all-empty row: zeros
+      if (0.f > best) {
+        best = 0.f;
+        if (WANT_ARG) *arg_row = -1;
+      }
+      continue;
+    }
+    const int q = cl * nrows + (h - g.h_lo);
+    const int p_lo = t.plo[q];
+    const int x0 = ((g.c0 + cl) * H + h) * W - p_lo * C;  // flat index of column 0 relative to pixel p_lo
+    int ch = x0 + wa, d = 0;
+    while (ch >= C) {  // <= max_pix - 1 steps, once per row
+      ch -= C;
+      ++d;
+    }
+    for (int w = wa; w < wb;) {  // the <= pk cells of this row lie in one or two pixels: one head test per pixel
+      const int span = min(wb - w, C - ch);
+      const int head = t.heads[q * max_pix + d];
+      if (head < 0) {  // a run of empty zeros; only its first cell can take the lead
+        if (0.f > best) {
+          best = 0.f;
+          if (WANT_ARG) *arg_row = -1;
+        }
+      } else {
+        for (int k = 0; k < span; ++k) {
+          const float v = cell_value(head, ch + k, C, policy, feats, next);
+          if (v > best) {
+            best = v;
+            if (WANT_ARG) {
+              *arg_row = (policy == LG_BEV_LAST) ? head : -2 - head;  // MAX: resolve the chain lazily
+              *arg_ch = ch + k;
+            }
+          }
+        }
+      }
+      w += span;
+      ch = 0;
+      ++d;
+    }
+  }
+  return best;
+}
+
+__device__ __forceinline__ int64_t out_index(int layout, int b, int c, int i, int j, int C, int h_out, int w_out) {
+  return layout ? (((int64_t)b * h_out + i) * w_out + j) * C + c : (((int64_t)b * C + c) * h_out + i) * w_out + j;
+}
+
+// staged tile <-> global, coalesced for the layout (NHWC: c' fastest, NCHW: j fastest)
+template <bool STORE>
+__device__ __forceinline__ void tile_transfer(const TileGeom& g, float* s_out, float* gptr, int layout, int C, int h_out,
+                                              int w_out, bool zero) {
+  static_assert(kCG == 32 && kJC == 32 && kIB == 8, "index decomposition below assumes 32 x 8 x 32 tiles");
+  for (int e = threadIdx.x; e < kIB * kJC * kCG; e += blockDim.x) {
+    int cl, il, jl;
+    if (layout) {
+      cl = e & 31, jl = (e >> 5) & 31, il = e >> 10;
+    } else {
+      jl = e & 31, il = (e >> 5) & 7, cl = e >> 8;
+    }
+    if (cl >= g.ncg || il >= g.nib || jl >= g.njc) continue;
+    const int se = (il * kJC + jl) * kPitch + cl;
+    const int64_t ge = out_index(layout, g.b, g.c0 + cl, g.i0 + il, g.j0 + jl, C, h_out, w_out);
+    if (STORE)
+      gptr[ge] = zero ? 0.f : s_out[se];
+    else
+      s_out[se] = gptr[ge];
+  }
 }
 
 __global__ void __launch_bounds__(256)
     k_bev_pool_fwd(const float* __restrict__ feats, const int* __restrict__ next, const int* __restrict__ pixmap, int C,
-                   int H, int W, int h_out, int w_out, int pk, int ps, int pp, int policy, float* __restrict__ out) {
-  extern __shared__ float sm[];
-  const RowGeom g = row_geom(C, H, W, h_out, pk, ps, pp);
-  float* orow = out + (((int64_t)g.b * C + g.cp) * h_out + g.i) * w_out;
-  if (!load_rows(g, C, H, W, policy, feats, next, pixmap, sm)) {
-    for (int j = threadIdx.x; j < w_out; j += blockDim.x) orow[j] = 0.f;
+                   int H, int W, int h_out, int w_out, int pk, int ps, int pp, int policy, int layout, int max_pix,
+                   int pairs_cap, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const TileSmem t = carve_tile(s_dyn, pairs_cap, max_pix);
+  const TileGeom g = tile_geom(C, H, W, h_out, w_out, pk, ps, pp);
+  if (!tile_lookup(g, t, C, H, W, max_pix, pixmap)) {
+    tile_transfer<true>(g, t.out, out, layout, C, h_out, w_out, true);
     return;
   }
-  for (int j = threadIdx.x; j < w_out; j += blockDim.x) {
-    const int w0 = max(j * ps - pp, 0), w1 = min(j * ps - pp + pk, W);
-    float best = -INFINITY;
-    for (int r = 0; r < g.rows; ++r)
-      for (int w = w0; w < w1; ++w) best = fmaxf(best, sm[r * W + w]);
-    orow[j] = best;
+  // a warp takes one (c', i) row of windows at a time, lane = column: the 32 windows share their scrambled
+  // rows (an all-empty row set is detected once per warp) and neighbouring lanes read neighbouring cells
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < kCG * kIB; r += 8) {
+    const int cl = r >> 3, il = r & 7;
+    if (cl >= g.ncg || il >= g.nib) continue;
+    float v = 0.f;
+    if (lane < g.njc)
+      v = window_scan<false>(g, t, cl, g.i0 + il, g.j0 + lane, C, H, W, pk, ps, pp, max_pix, policy, feats, next,
+                             nullptr, nullptr);
+    t.out[(il * kJC + lane) * kPitch + cl] = v;
   }
+  __syncthreads();
+  tile_transfer<true>(g, t.out, out, layout, C, h_out, w_out, false);
 }
 
+// Backward: the gradient of each window goes to its first arg-max in scan order (max_pool2d backward) if
+// that cell holds a voxel.  A cell sits in <= ceil(pk/ps)^2 windows, possibly of different CTAs, so the
+// <= 4 contributions meet in grad_feats through float atomics (summation order of <= 4 terms: 1e-6
+// relative, the tolerance of the parity test).
 __global__ void __launch_bounds__(256)
     k_bev_pool_bwd(const float* __restrict__ feats, const int* __restrict__ next, const int* __restrict__ pixmap, int C,
-                   int H, int W, int h_out, int w_out, int pk, int ps, int pp, int policy,
-                   const float* __restrict__ grad_out, float* __restrict__ grad_feats) {
-  extern __shared__ float sm[];
-  const RowGeom g = row_geom(C, H, W, h_out, pk, ps, pp);
-  if (!load_rows(g, C, H, W, policy, feats, next, pixmap, sm)) return;
-  const float* grow = grad_out + (((int64_t)g.b * C + g.cp) * h_out + g.i) * w_out;
-  // first arg-max (scan order: row, then column; strictly greater) of each window
-  constexpr int kMaxPerThread = 8;
-  int arg[kMaxPerThread];
-  float gv[kMaxPerThread];
-  int cnt = 0;
-  for (int j = threadIdx.x; j < w_out && cnt < kMaxPerThread; j += blockDim.x, ++cnt) {
-    const int w0 = max(j * ps - pp, 0), w1 = min(j * ps - pp + pk, W);
-    float best = -INFINITY;
-    int a = -1;
-    for (int r = 0; r < g.rows; ++r)
-      for (int w = w0; w < w1; ++w) {
-        const float v = sm[r * W + w];
-        if (v > best) {
-          best = v;
-          a = r * W + w;
-        }
-      }
-    arg[cnt] = a;
-    gv[cnt] = grow[j];
-  }
+                   int H, int W, int h_out, int w_out, int pk, int ps, int pp, int policy, int layout, int max_pix,
+                   int pairs_cap, const float* __restrict__ grad_out, float* __restrict__ grad_feats) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const TileSmem t = carve_tile(s_dyn, pairs_cap, max_pix);
+  const TileGeom g = tile_geom(C, H, W, h_out, w_out, pk, ps, pp);
+  if (!tile_lookup(g, t, C, H, W, max_pix, pixmap)) return;
+  tile_transfer<false>(g, t.out, const_cast<float*>(grad_out), layout, C, h_out, w_out, false);
   __syncthreads();
-  for (int64_t e = threadIdx.x; e < g.cells; e += blockDim.x) sm[e] = 0.f;
-  __syncthreads();
-  for (int q = 0; q < cnt; ++q)
-    if (arg[q] >= 0 && gv[q] != 0.f) atomicAdd(&sm[arg[q]], gv[q]);
-  __syncthreads();
-  const int* pm = pixmap + (int64_t)g.b * H * W;
-  for (int64_t e = threadIdx.x; e < g.cells; e += blockDim.x) {
-    const float gsum = sm[e];
-    if (gsum == 0.f) continue;
-    const int64_t m = g.m_lo + e;
-    const int64_t p = m / C;
-    const int ch = (int)(m - p * C);
-    const int row = cell_argrow(__ldg(pm + p), ch, C, policy, feats, next);
-    if (row >= 0) atomicAdd(grad_feats + (int64_t)row * C + ch, gsum);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < kCG * kIB; r += 8) {
+    const int cl = r >> 3, il = r & 7, jl = lane;
+    if (cl >= g.ncg || il >= g.nib || jl >= g.njc) continue;
+    const float gv = t.out[(il * kJC + jl) * kPitch + cl];
+    if (gv == 0.f) continue;
+    int row = -1, ch = 0;
+    window_scan<true>(g, t, cl, g.i0 + il, g.j0 + jl, C, H, W, pk, ps, pp, max_pix, policy, feats, next, &row, &ch);
+    if (row == -1) continue;
+    if (row < -1) row = cell_argrow(-2 - row, ch, C, policy, feats, next);
+    atomicAdd(grad_feats + (int64_t)row * C + ch, gv);
   }
 }
 
@@ -215,12 +332,26 @@ __global__ void k_fill_i32_bev(int* p, int64_t n, int v) {
 
 using namespace lg;
 
+// a (c', h') run of a tile spans (kJC-1)*ps+pk floats = at most this many pixels of C channels
+static int bev_max_pix(int C, int pk, int ps) { return ((kJC - 1) * ps + pk + C - 2) / C + 1; }
+static int bev_pairs_cap(int C, int pk, int ps) { return (C < kCG ? C : kCG) * ((kIB - 1) * ps + pk); }
+static size_t bev_smem_bytes(int C, int pk, int ps) {  // staged tile + heads + first pixels + row masks
+  const size_t pairs = bev_pairs_cap(C, pk, ps);
+  return sizeof(float) * kIB * kJC * kPitch + sizeof(int) * pairs * (bev_max_pix(C, pk, ps) + 1) + sizeof(int) * kCG + 16;
+}
+static int64_t bev_tiles(int B, int C, int h_out, int w_out) {
+  return (int64_t)B * ceil_div(C, kCG) * ceil_div(h_out, kIB) * ceil_div(w_out, kJC);
+}
+
 static int bev_check(int64_t n, int C, int B, int H, int W, int pk, int ps, int pp, int policy, const char* who) {
   LG_CHECK_ARG(n >= 0 && C >= 1 && B >= 1 && H >= 1 && W >= 1, "%s: bad sizes", who);
   LG_CHECK_ARG(pk >= 1 && ps >= 1 && pp >= 0 && 2 * pp <= pk, "%s: bad pooling parameters", who);
   LG_CHECK_ARG(policy == LG_BEV_LAST || policy == LG_BEV_MAX, "%s: bad policy", who);
   LG_CHECK_ARG((int64_t)B * H * W < ((int64_t)1 << 31), "%s: batch*H*W exceeds int32", who);
-  LG_CHECK_ARG((size_t)pk * W * sizeof(float) <= 200 * 1024, "%s: pk*W too large for shared memory", who);
+  LG_CHECK_ARG((kIB - 1) * ps + pk <= 32, "%s: pool stride/kernel too large for the row mask", who);
+  LG_CHECK_ARG((int64_t)C * H * W < ((int64_t)1 << 31), "%s: C*H*W exceeds int32", who);
+  LG_CHECK_ARG(bev_smem_bytes(C, pk, ps) <= 200 * 1024, "%s: C=%d too small for pool stride %d (shared memory)", who, C,
+               ps);
   return LG_OK;
 }
 
@@ -230,7 +361,8 @@ extern "C" size_t lg_bev_workspace(int64_t n, int32_t batch_size, int32_t H, int
 
 extern "C" int lg_bev_forward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size,
                               float bound, float voxel_size, int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp,
-                              int32_t policy, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+                              int32_t policy, int32_t layout, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = bev_check(n, C, batch_size, H, W, pk, ps, pp, policy, "lg_bev_forward");
   if (rc) return rc;
@@ -246,20 +378,22 @@ extern "C" int lg_bev_forward(const int32_t* coords4, const float* feats, int64_
                                                                  w.pixmap);
     LG_LAUNCH_OK();
   }
-  const size_t smem = (size_t)pk * W * sizeof(float);
+  LG_CHECK_ARG(layout == 0 || layout == 1, "lg_bev_forward: layout must be 0 (NCHW) or 1 (NHWC)");
+  const size_t smem = bev_smem_bytes(C, pk, ps);
+  const int64_t blocks = bev_tiles(batch_size, C, h_out, w_out);
+  LG_CHECK_ARG(blocks < ((int64_t)1 << 31), "lg_bev_forward: too many output tiles");
   LG_CUDA_OK(cudaFuncSetAttribute(k_bev_pool_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = (int64_t)batch_size * C * h_out;
-  LG_CHECK_ARG(blocks < ((int64_t)1 << 31), "lg_bev_forward: too many output rows");
   k_bev_pool_fwd<<<(unsigned)blocks, 256, smem, stream>>>(feats, w.next, w.pixmap, C, H, W, h_out, w_out, pk, ps, pp,
-                                                          policy, out);
+                                                          policy, layout, bev_max_pix(C, pk, ps), bev_pairs_cap(C, pk, ps),
+                                                          out);
   LG_LAUNCH_OK();
   return LG_OK;
 }
 
 extern "C" int lg_bev_backward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size,
                                int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy,
-                               const float* grad_out, float* grad_feats, const void* workspace, size_t workspace_bytes,
-                               void* stream_) {
+                               int32_t layout, const float* grad_out, float* grad_feats, const void* workspace,
+                               size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = bev_check(n, C, batch_size, H, W, pk, ps, pp, policy, "lg_bev_backward");
   if (rc) return rc;
@@ -269,13 +403,15 @@ extern "C" int lg_bev_backward(const int32_t* coords4, const float* feats, int64
   if (n == 0) return LG_OK;
   LG_CHECK_ARG(feats && grad_out && grad_feats, "lg_bev_backward: null pointer");
   const int h_out = (H + 2 * pp - pk) / ps + 1, w_out = (W + 2 * pp - pk) / ps + 1;
-  LG_CHECK_ARG(w_out <= 8 * 256, "lg_bev_backward: output rows wider than 2048 are not supported");
+  LG_CHECK_ARG(layout == 0 || layout == 1, "lg_bev_backward: layout must be 0 (NCHW) or 1 (NHWC)");
   LG_CUDA_OK(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)n * C, stream));
-  const size_t smem = (size_t)pk * W * sizeof(float);
+  const size_t smem = bev_smem_bytes(C, pk, ps);
+  const int64_t blocks = bev_tiles(batch_size, C, h_out, w_out);
+  LG_CHECK_ARG(blocks < ((int64_t)1 << 31), "lg_bev_backward: too many output tiles");
   LG_CUDA_OK(cudaFuncSetAttribute(k_bev_pool_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = (int64_t)batch_size * C * h_out;
   k_bev_pool_bwd<<<(unsigned)blocks, 256, smem, stream>>>(feats, w.next, w.pixmap, C, H, W, h_out, w_out, pk, ps, pp,
-                                                          policy, grad_out, grad_feats);
+                                                          policy, layout, bev_max_pix(C, pk, ps), bev_pairs_cap(C, pk, ps),
+                                                          grad_out, grad_feats);
   LG_LAUNCH_OK();
   if (policy == LG_BEV_LAST) {
     k_bev_dup_grad<<<(unsigned)ceil_div(n * C, 256), 256, 0, stream>>>(w.pix_of_row, w.pixmap, n, C, grad_feats);

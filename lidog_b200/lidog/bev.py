@@ -28,7 +28,7 @@ def image_size(bound: float, voxel_size: float) -> int:
 
 class BevProjectFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, coords, batch_size, bound, voxel_size, pool, policy):
+    def forward(ctx, feats, coords, batch_size, bound, voxel_size, pool, policy, channels_last):
         L = cabi.lib()
         feats_c = feats.detach().contiguous()
         coords = coords.contiguous()
@@ -37,12 +37,13 @@ class BevProjectFunction(torch.autograd.Function):
         pk, ps, pp = pool
         h = (H + 2 * pp - pk) // ps + 1
         w = (W + 2 * pp - pk) // ps + 1
-        out = torch.empty((batch_size, C, h, w), dtype=torch.float32, device=feats.device)
+        out = torch.empty((batch_size, C, h, w), dtype=torch.float32, device=feats.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
         ws_bytes = L.lg_bev_workspace(n, batch_size, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
         cabi.check(L.lg_bev_forward(cabi.ptr(coords), cabi.ptr(feats_c), n, C, batch_size, float(bound),
-                                    float(voxel_size), H, W, pk, ps, pp, policy, cabi.ptr(out), cabi.ptr(ws), ws_bytes,
-                                    cabi.stream()), "lg_bev_forward")
+                                    float(voxel_size), H, W, pk, ps, pp, policy, 1 if channels_last else 0,
+                                    cabi.ptr(out), cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_bev_forward")
         ctx.save_for_backward(feats_c, coords, ws)
         ctx.args = (n, C, batch_size, H, W, pk, ps, pp, policy, ws_bytes)
         return out
@@ -51,35 +52,33 @@ class BevProjectFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         feats, coords, ws = ctx.saved_tensors
         n, C, batch_size, H, W, pk, ps, pp, policy, ws_bytes = ctx.args
-        grad_out = grad_out.contiguous()
+        # consume the gradient in the memory order it arrives in (cuDNN hands back channels_last)
+        nhwc = grad_out.dim() == 4 and grad_out.is_contiguous(memory_format=torch.channels_last) \
+            and not grad_out.is_contiguous()
+        if not nhwc:
+            grad_out = grad_out.contiguous()
         grad_feats = torch.empty((n, C), dtype=torch.float32, device=feats.device)
         cabi.check(cabi.lib().lg_bev_backward(cabi.ptr(coords), cabi.ptr(feats), n, C, batch_size, H, W, pk, ps, pp,
-                                              policy, cabi.ptr(grad_out), cabi.ptr(grad_feats), cabi.ptr(ws), ws_bytes,
-                                              cabi.stream()), "lg_bev_backward")
-        return grad_feats, None, None, None, None, None, None
+                                              policy, 1 if nhwc else 0, cabi.ptr(grad_out), cabi.ptr(grad_feats),
+                                              cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_bev_backward")
+        return grad_feats, None, None, None, None, None, None, None
 
 
-def bev_project(coords, feats, batch_size, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last"):
+def bev_project(coords, feats, batch_size, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last",
+                channels_last=False):
     return BevProjectFunction.apply(feats, coords, int(batch_size), float(bound), float(voxel_size), tuple(pool),
-                                    POLICIES[policy])
+                                    POLICIES[policy], bool(channels_last))
 
 
 def sparse2super(x, bound=50.0, voxel_size=0.05, pool=(5, 3, 1), policy="last", batch_size=None):
     """x: SparseTensor (any tensor stride; coordinates in stride-1 voxel units) -> [B, C, h, w]."""
-    out = _sparse2super(x, bound, voxel_size, pool, policy, batch_size)
-    if CONFIG["channels_last"]:
-        out = out.contiguous(memory_format=torch.channels_last)
-    return out
-
-
-def _sparse2super(x, bound, voxel_size, pool, policy, batch_size):
     cm = x.coordinate_manager
     if batch_size is None:
         batch_size = getattr(cm, "batch_size", None)
     if batch_size is None:  # reference: batch_bottle_idx.max()+1 (minkunet_bev.py:193); one host sync, cached
         batch_size = int(x.C[:, 0].max().item()) + 1
         cm.batch_size = batch_size
-    return bev_project(x.C, x.F, batch_size, bound, voxel_size, pool, policy)
+    return bev_project(x.C, x.F, batch_size, bound, voxel_size, pool, policy, CONFIG["channels_last"])
 
 
 def patch_reference_model(model, policy="last"):

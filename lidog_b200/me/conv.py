@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import cabi
+from ._grad16 import take_grad16
 from .sparse_tensor import SparseTensor
 
 # operand format of the tensor-core path: "fp16" (default; 2^-11 unit round-off meets the 1e-3 bar),
@@ -130,12 +131,16 @@ class SparseConvFunction(torch.autograd.Function):
         if ctx.tc:
             (x16,) = ctx.saved_tensors
             fmt = ctx.fmt
-            scale = None
-            if fmt == cabi.FMT_FP16:  # bring the gradient into fp16's normal range (power-of-two scale)
-                scale = torch.empty(4, dtype=torch.float32, device=dy.device)
-                cabi.check(L.lg_absmax_scale(cabi.ptr(dy), dy.numel(), cabi.ptr(scale), cabi.stream()),
-                           "lg_absmax_scale")
-            dy16 = _cast16(dy, fmt, scale)
+            hit = take_grad16(dy, fmt)  # the fused BN backward already wrote the scaled 16-bit gradient
+            if hit is not None:
+                dy16, scale = hit
+            else:
+                scale = None
+                if fmt == cabi.FMT_FP16:  # bring the gradient into fp16's normal range (power-of-two scale)
+                    scale = torch.empty(4, dtype=torch.float32, device=dy.device)
+                    cabi.check(L.lg_absmax_scale(cabi.ptr(dy), dy.numel(), cabi.ptr(scale), cabi.stream()),
+                               "lg_absmax_scale")
+                dy16 = _cast16(dy, fmt, scale)
             inv = None if scale is None else scale[1:]
             if ctx.needs_input_grad[0]:
                 dx = _gemm_tc(p_dgrad, dy16, ctx.w16, cin, flip, fmt, inv, None)

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from .. import cabi
+from . import _grad16
 
 
 def _check_count(count_status: torch.Tensor, what: str) -> int:
@@ -78,6 +79,7 @@ def _round_up(a, b):
 
 class CoordinateManager:
     def __init__(self, coordinates: torch.Tensor):
+        _grad16.clear()  # a new batch: no gradient of the previous one is still wanted
         res = coords_unique(coordinates, 1)
         self.device = coordinates.device
         self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}
@@ -90,6 +92,7 @@ class CoordinateManager:
     def from_quantized(cls, res: dict):
         """Adopt the table built by sparse_quantize(_batch): voxelisation and the network share ONE
         hashed voxel index (no second hash build for ME.SparseTensor)."""
+        _grad16.clear()
         self = cls.__new__(cls)
         self.device = res["coords"].device
         self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}

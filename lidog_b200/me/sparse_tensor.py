@@ -120,4 +120,9 @@ def cat(*tensors):
     t0 = tensors[0]
     for t in tensors[1:]:
         t0._same_map(t)
-    return t0._like(torch.cat([t.F for t in tensors], dim=1))
+    out = t0._like(torch.cat([t.F for t in tensors], dim=1))
+    caches = [t._f16_cache for t in tensors]
+    if all(c is not None and c[0] == (caches[0][0][0], t.F._version, t.F.data_ptr()) for c, t in zip(caches, tensors)):
+        f = out._F  # the 16-bit operand copies concatenate too: no cast pass for the block that follows
+        out._f16_cache = ((caches[0][0][0], f._version, f.data_ptr()), torch.cat([c[1] for c in caches], dim=1))
+    return out

@@ -64,3 +64,29 @@ def test_bev_96_channels_kitti_shape(cuda):
     ref, _ = ob.bev_forward(coords, feats, 1, 50.0, policy="last")
     out, _ = _run(cuda, coords, feats, 1, 50.0, "last")
     assert out.shape == (1, 96, 666, 666) and np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("policy", ["last", "max"])
+def test_bev_channels_last_layout_is_the_same_tensor(cuda, policy):
+    """layout 1 (NHWC / channels_last): same logical values and gradients as the NCHW layout, bit for bit in
+    the forward; the backward consumes a channels_last gradient without a copy."""
+    from lidog_b200.lidog.bev import bev_project
+    rng = np.random.default_rng(13)
+    import tests.golden.make_bev_golden as mk
+    coords, feats = mk.make_case(rng, 5000, 2, 6.0, 40, dup_frac=0.4)  # 40 channels: a partial channel group
+    c = torch.from_numpy(coords).to(cuda)
+    outs, grads = [], []
+    gw = None
+    for cl in (False, True):
+        f = torch.from_numpy(feats).to(cuda).requires_grad_(True)
+        out = bev_project(c, f, 2, 6.0, 0.05, (5, 3, 1), policy, channels_last=cl)
+        assert out.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+        if gw is None:
+            gw = torch.from_numpy(rng.standard_normal(tuple(out.shape)).astype(np.float32)).to(cuda)
+        out.backward(gw.contiguous(memory_format=torch.channels_last) if cl else gw)
+        outs.append(out.detach().cpu().numpy())
+        grads.append(f.grad.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(grads[0] - grads[1]).max() <= 1e-6 * max(1.0, np.abs(grads[0]).max())
+    ref, ctx = ob.bev_forward(coords, feats, 2, 6.0, policy=policy)
+    assert np.array_equal(outs[1], ref)
