@@ -182,7 +182,7 @@ int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const
  * exchanges (the caller all-reduces `sums` and `count`).  C % 4 == 0, C <= 1024.  Deterministic.
  *   stats float[4C] = [mean, invstd, scale = gamma*invstd, shift = beta - mean*scale] */
 size_t lg_bn_workspace(int64_t n, int32_t C);
-/* sums double[2C] = [sum x, sum x^2] of this rank's n rows. */
+/* sums double[2C + 1] = [sum x, sum x^2, n] of this rank's n rows. */
 int lg_bn_stats(const float* x, int64_t n, int32_t C, double* sums, void* workspace, size_t workspace_bytes,
                 void* stream);
 /* count = rows over all ranks (read from the device double *count_dev when that is non-NULL: the all-reduced
@@ -213,6 +213,17 @@ int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, const float
                     const float* x2, const float* stats2, const float* coef2, int32_t relu, int64_t n, int32_t C,
                     float* dx, void* dx16, const float* scale, float* dx2, void* dx2_16, const float* scale2,
                     float* dres, void* dres16, const float* scale_r, int32_t fmt, void* stream);
+
+/* ------------------------------------------------------------------ SyncBN exchange over peer memory
+ *
+ * train_lidog.py:228 converts every MinkowskiBatchNorm to SyncBN: 124 latency-bound exchanges of <= 3C doubles per
+ * step.  lg_peer_sum replaces the NCCL call of each: one kernel publishes this rank's vector in its exchange
+ * buffer, raises an epoch flag and adds the peers' vectors read over NVLink, in rank order (bit-identical on all
+ * ranks).  peer_bufs: HOST array of `world` device addresses (in this process) of every rank's exchange buffer of
+ * lg_peer_exchange_bytes() bytes, zero-initialised (torch symmetric memory / cudaIpc mappings). */
+size_t lg_peer_exchange_bytes(void);
+int lg_peer_sum(const double* local, int32_t n, void* const* peer_bufs, int32_t world, int32_t rank, uint64_t epoch,
+                double* out, void* stream);
 
 /* ------------------------------------------------------------------ BEV projection */
 

@@ -63,6 +63,8 @@ SIGNATURES = {
     "lg_bn_bwd_gscale": (C.c_int, [_vp, _i32, _vp, _vp]),
     "lg_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _i32, _vp]),
+    "lg_peer_exchange_bytes": (_sz, []),
+    "lg_peer_sum": (C.c_int, [_vp, _i32, C.POINTER(C.c_void_p), _i32, _i32, C.c_uint64, _vp, _vp]),
     "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32]),
     "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _vp]),
@@ -79,7 +81,7 @@ KERNELS_PER_CALL = {
     "lg_absmax_scale": 2, "lg_prep_weights": 1, "lg_conv_gemm_tc": 1, "lg_conv_wgrad_tc": 2,
     "lg_bev_forward": 2, "lg_bev_backward": 3,
     "lg_bn_stats": 2, "lg_bn_finalize": 1, "lg_bn_apply": 1, "lg_bn_bwd_stats": 2, "lg_bn_bwd_finalize": 1,
-    "lg_bn_bwd_gscale": 1, "lg_bn_bwd_apply": 1,
+    "lg_bn_bwd_gscale": 1, "lg_bn_bwd_apply": 1, "lg_peer_sum": 1,
 }
 COUNTS: dict = {}
 

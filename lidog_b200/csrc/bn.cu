@@ -107,9 +107,10 @@ constexpr int kRedX = 128, kRedY = 8;
 
 // partial [n_partials][width] (float) -> sums [width] (double)
 __global__ void __launch_bounds__(kRedX * kRedY)
-    k_bn_reduce(const float* __restrict__ partial, int n_partials, int width, double* __restrict__ sums) {
+    k_bn_reduce(const float* __restrict__ partial, int n_partials, int width, double* __restrict__ sums, double tail) {
   __shared__ double sm[kRedY][kRedX];
   const int c = blockIdx.x * kRedX + threadIdx.x;
+  if (c == 0 && threadIdx.y == 0) sums[width] = tail;  // the row count rides along (SyncBN sums it too)
   double a = 0.0;
   if (c < width)
     for (int p = threadIdx.y; p < n_partials; p += kRedY) a += (double)partial[(size_t)p * width + c];
@@ -170,29 +171,44 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, double count, con
   }
 }
 
-// y = act(x * scale + shift [+ x2 * scale2 + shift2] [+ res]); st = [mean, invstd, scale, shift] x C
+// y = act(x * scale + shift [+ x2 * scale2 + shift2] [+ res]); st = [mean, invstd, scale, shift] x C.
+// A thread handles kApplyU float4 a block-width apart: all loads are issued before the first use, so a CTA
+// keeps 4x the bytes in flight of the one-element-per-thread form (HBM-latency bound otherwise).
+constexpr int kApplyU = 4;
 __global__ void __launch_bounds__(256)
     k_bn_apply(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ x2,
                const float* __restrict__ st2, const float* __restrict__ res, int relu, int64_t n4, int C,
                float* __restrict__ y, unsigned short* __restrict__ y16, int fmt) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)(i % (C >> 2)) * 4;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-  const float4 sc = *reinterpret_cast<const float4*>(st + 2 * C + c), sh = *reinterpret_cast<const float4*>(st + 3 * C + c);
-  float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-  if (x2) {
-    const float4 v2 = __ldg(reinterpret_cast<const float4*>(x2) + i);
-    const float4 s2 = *reinterpret_cast<const float4*>(st2 + 2 * C + c), h2 = *reinterpret_cast<const float4*>(st2 + 3 * C + c);
-    o.x += fmaf(v2.x, s2.x, h2.x), o.y += fmaf(v2.y, s2.y, h2.y), o.z += fmaf(v2.z, s2.z, h2.z), o.w += fmaf(v2.w, s2.w, h2.w);
+  const int64_t base = (int64_t)blockIdx.x * (256 * kApplyU) + threadIdx.x;
+  const int Cq = C >> 2;
+  float4 v[kApplyU], v2[kApplyU], r[kApplyU];
+#pragma unroll
+  for (int u = 0; u < kApplyU; ++u) {
+    const int64_t i = base + u * 256;
+    if (i < n4) {
+      v[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
+      if (x2) v2[u] = __ldg(reinterpret_cast<const float4*>(x2) + i);
+      if (res) r[u] = __ldg(reinterpret_cast<const float4*>(res) + i);
+    }
   }
-  if (res) {
-    const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
-    o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+#pragma unroll
+  for (int u = 0; u < kApplyU; ++u) {
+    const int64_t i = base + u * 256;
+    if (i >= n4) break;
+    const int c = (int)(i % Cq) * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(st + 2 * C + c), sh = *reinterpret_cast<const float4*>(st + 3 * C + c);
+    float4 o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z),
+                           fmaf(v[u].w, sc.w, sh.w));
+    if (x2) {
+      const float4 s2 = *reinterpret_cast<const float4*>(st2 + 2 * C + c), h2 = *reinterpret_cast<const float4*>(st2 + 3 * C + c);
+      o.x += fmaf(v2[u].x, s2.x, h2.x), o.y += fmaf(v2[u].y, s2.y, h2.y), o.z += fmaf(v2[u].z, s2.z, h2.z),
+          o.w += fmaf(v2[u].w, s2.w, h2.w);
+    }
+    if (res) o.x += r[u].x, o.y += r[u].y, o.z += r[u].z, o.w += r[u].w;
+    if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+    reinterpret_cast<float4*>(y)[i] = o;
+    if (y16) store16x4(y16 + i * 4, o, fmt);
   }
-  if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-  reinterpret_cast<float4*>(y)[i] = o;
-  if (y16) store16x4(y16 + i * 4, o, fmt);
 }
 
 __device__ __forceinline__ float4 masked(float4 dy, float4 y, int relu) {
@@ -304,6 +320,7 @@ __global__ void k_bn_gscale(const float* __restrict__ maxes, int C, float* __res
   }
 }
 
+constexpr int kBwdU = 2;
 __global__ void __launch_bounds__(256)
     k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                    const float* __restrict__ st, const float* __restrict__ coef, const float* __restrict__ x2,
@@ -312,43 +329,51 @@ __global__ void __launch_bounds__(256)
                    float* __restrict__ dx2, unsigned short* __restrict__ dx2_16, const float* __restrict__ scale2,
                    float* __restrict__ dres, unsigned short* __restrict__ dres16, const float* __restrict__ scale_r,
                    int fmt) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)(i % (C >> 2)) * 4;
+  const int64_t base = (int64_t)blockIdx.x * (256 * kBwdU) + threadIdx.x;
+  const int Cq = C >> 2;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 g = masked(__ldg(reinterpret_cast<const float4*>(dy) + i),
-                          relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z, relu);
-  {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    const float4 mu = *reinterpret_cast<const float4*>(st + c);
-    const float4 a = *reinterpret_cast<const float4*>(coef + c), b = *reinterpret_cast<const float4*>(coef + C + c),
-                 k = *reinterpret_cast<const float4*>(coef + 2 * C + c);
-    const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
-                                 fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
-    reinterpret_cast<float4*>(dx)[i] = o;
-    if (dx16) {
-      const float s = scale ? scale[0] : 1.f;
-      store16x4(dx16 + i * 4, make_float4(o.x * s, o.y * s, o.z * s, o.w * s), fmt);
+  float4 gd[kBwdU], gy[kBwdU], vx[kBwdU], vx2[kBwdU];
+#pragma unroll
+  for (int u = 0; u < kBwdU; ++u) {
+    const int64_t i = base + u * 256;
+    if (i < n4) {
+      gd[u] = __ldg(reinterpret_cast<const float4*>(dy) + i);
+      gy[u] = relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z;
+      vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
+      if (x2) vx2[u] = __ldg(reinterpret_cast<const float4*>(x2) + i);
     }
   }
-  if (x2) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x2) + i);
-    const float4 mu = *reinterpret_cast<const float4*>(st2 + c);
-    const float4 a = *reinterpret_cast<const float4*>(coef2 + c), b = *reinterpret_cast<const float4*>(coef2 + C + c),
-                 k = *reinterpret_cast<const float4*>(coef2 + 2 * C + c);
-    const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
-                                 fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
-    reinterpret_cast<float4*>(dx2)[i] = o;
-    if (dx2_16) {
-      const float s = scale2 ? scale2[0] : 1.f;
-      store16x4(dx2_16 + i * 4, make_float4(o.x * s, o.y * s, o.z * s, o.w * s), fmt);
+  const float s1 = (dx16 && scale) ? scale[0] : 1.f, s2 = (dx2_16 && scale2) ? scale2[0] : 1.f,
+              sr = (dres16 && scale_r) ? scale_r[0] : 1.f;
+#pragma unroll
+  for (int u = 0; u < kBwdU; ++u) {
+    const int64_t i = base + u * 256;
+    if (i >= n4) break;
+    const int c = (int)(i % Cq) * 4;
+    const float4 g = masked(gd[u], gy[u], relu);
+    {
+      const float4 v = vx[u];
+      const float4 mu = *reinterpret_cast<const float4*>(st + c);
+      const float4 a = *reinterpret_cast<const float4*>(coef + c), b = *reinterpret_cast<const float4*>(coef + C + c),
+                   k = *reinterpret_cast<const float4*>(coef + 2 * C + c);
+      const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
+                                   fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
+      reinterpret_cast<float4*>(dx)[i] = o;
+      if (dx16) store16x4(dx16 + i * 4, make_float4(o.x * s1, o.y * s1, o.z * s1, o.w * s1), fmt);
     }
-  }
-  if (dres) {
-    reinterpret_cast<float4*>(dres)[i] = g;
-    if (dres16) {
-      const float s = scale_r ? scale_r[0] : 1.f;
-      store16x4(dres16 + i * 4, make_float4(g.x * s, g.y * s, g.z * s, g.w * s), fmt);
+    if (x2) {
+      const float4 v = vx2[u];
+      const float4 mu = *reinterpret_cast<const float4*>(st2 + c);
+      const float4 a = *reinterpret_cast<const float4*>(coef2 + c), b = *reinterpret_cast<const float4*>(coef2 + C + c),
+                   k = *reinterpret_cast<const float4*>(coef2 + 2 * C + c);
+      const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
+                                   fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
+      reinterpret_cast<float4*>(dx2)[i] = o;
+      if (dx2_16) store16x4(dx2_16 + i * 4, make_float4(o.x * s2, o.y * s2, o.z * s2, o.w * s2), fmt);
+    }
+    if (dres) {
+      reinterpret_cast<float4*>(dres)[i] = g;
+      if (dres16) store16x4(dres16 + i * 4, make_float4(g.x * sr, g.y * sr, g.z * sr, g.w * sr), fmt);
     }
   }
 }
@@ -372,7 +397,7 @@ using namespace lg;
 // workspace: per-block partials of the widest reduction (6 C floats per block)
 extern "C" size_t lg_bn_workspace(int64_t n, int32_t C) { return sizeof(float) * (size_t)kBnMaxBlocks * 6 * C + 256; }
 
-/* sums double[2C] = [sum x, sum x^2] over the n rows (this rank). */
+/* sums double[2C + 1] = [sum x, sum x^2, n] over the n rows (this rank). */
 extern "C" int lg_bn_stats(const float* x, int64_t n, int32_t C, double* sums, void* workspace, size_t workspace_bytes,
                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -382,7 +407,8 @@ extern "C" int lg_bn_stats(const float* x, int64_t n, int32_t C, double* sums, v
   const int nb = bn_blocks(n);
   k_bn_stats<<<nb, kBnThreads, red_smem(C), stream>>>(x, n, C, (float*)workspace);
   LG_LAUNCH_OK();
-  k_bn_reduce<<<ceil_div(2 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>((const float*)workspace, nb, 2 * C, sums);
+  k_bn_reduce<<<ceil_div(2 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>((const float*)workspace, nb, 2 * C, sums,
+                                                                          (double)n);
   LG_LAUNCH_OK();
   return LG_OK;
 }
@@ -406,7 +432,7 @@ extern "C" int lg_bn_apply(const float* x, const float* stats, const float* x2, 
   if (rc) return rc;
   LG_CHECK_ARG(x && stats && y && (!x2 || stats2), "lg_bn_apply: null pointer");
   const int64_t n4 = n * (C >> 2);
-  k_bn_apply<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream_>>>(x, stats, x2, stats2, res, relu, n4, C, y,
+  k_bn_apply<<<(unsigned)ceil_div(n4, 256 * kApplyU), 256, 0, (cudaStream_t)stream_>>>(x, stats, x2, stats2, res, relu, n4, C, y,
                                                                              (unsigned short*)y16, fmt);
   LG_LAUNCH_OK();
   return LG_OK;
@@ -465,7 +491,7 @@ extern "C" int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, 
   LG_CHECK_ARG(dy && x && stats && coef && dx && (!relu || y) && (!x2 || (stats2 && coef2 && dx2)),
                "lg_bn_bwd_apply: null pointer");
   const int64_t n4 = n * (C >> 2);
-  k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream_>>>(
+  k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256 * kBwdU), 256, 0, (cudaStream_t)stream_>>>(
       dy, y, x, stats, coef, x2, stats2, coef2, relu, n4, C, dx, (unsigned short*)dx16, scale, dx2,
       (unsigned short*)dx2_16, scale2, dres, (unsigned short*)dres16, scale_r, fmt);
   LG_LAUNCH_OK();

@@ -54,9 +54,17 @@ def _group(bn):
     return None, 1
 
 
-class _Branch:
-    """What the backward needs about one BN of the fused expression."""
-    __slots__ = ("bn", "stats", "count", "pg")
+def _all_sum(v: torch.Tensor, pg) -> torch.Tensor:
+    """Sum of a float64 vector over the ranks of `pg`: the one-kernel peer-memory exchange (me/peer.py) when the
+    node offers symmetric memory, an NCCL all-reduce otherwise.  Returns a new tensor."""
+    from . import peer
+    ex = peer.get(pg)
+    out = torch.empty_like(v)
+    if ex is not None:
+        return ex.sum(v, out)
+    out.copy_(v)
+    torch.distributed.all_reduce(out, group=pg)
+    return out
 
 
 def _bn_statistics(x: torch.Tensor, bn, ws, ws_bytes):
@@ -68,9 +76,8 @@ def _bn_statistics(x: torch.Tensor, bn, ws, ws_bytes):
     cabi.check(L.lg_bn_stats(cabi.ptr(x), n, C, cabi.ptr(sums), cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_bn_stats")
     pg, world = _group(bn)
     count = float(n)  # a host number without SyncBN, a device scalar (never read back) with it
-    if pg is not None:  # SyncBN: one all-reduce of [sum x, sum x^2, n]
-        sums[2 * C:].fill_(float(n))
-        torch.distributed.all_reduce(sums, group=pg)
+    if pg is not None:  # SyncBN: one exchange of [sum x, sum x^2, n]
+        sums = _all_sum(sums, pg)
         count = sums[2 * C:]
     count_host, count_dev = (count, None) if isinstance(count, float) else (0.0, count)
     stats = torch.empty(4 * C, dtype=torch.float32, device=dev)
@@ -133,8 +140,7 @@ class FusedBNFunction(torch.autograd.Function):
         sums_g = sums
         pg = pg_a if pg_a is not None else pg_b
         if pg is not None:  # SyncBN: dx needs the sums over every rank; dgamma / dbeta stay local (DDP reduces them)
-            sums_g = sums.clone()
-            torch.distributed.all_reduce(sums_g, group=pg)  # (the fp16 bound only has to hold on this rank)
+            sums_g = _all_sum(sums, pg)  # (the fp16 bound only has to hold on this rank: maxes stay local)
         use16 = fmt is not None
         d16 = _dtype16(fmt) if use16 else None
 
