@@ -57,6 +57,24 @@ def peaks():
     return dict(hbm_gbs=6441.9, tf_sustained=1407.8, tf_burst=1669.9, source="measured (round-1 driver values recorded in SURVEY.md)")
 
 
+def ncu_traffic():
+    """DRAM bytes of one k_gemm2 launch from the committed `ncu --set full` capture (profiles/): read + write.
+    The capture is the block8 layer shape (tensor stride 1, 96 -> 96, batch 8 kitti-shaped scans)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_gemm2.txt")))
+    if not files:
+        return None, None
+    txt = open(files[-1]).read()
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(re.escape(key) + r" = ([0-9.]+) (\w+)", txt)
+        if not m:
+            return None, None
+        tot += float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m.group(2)]
+    return tot, os.path.basename(files[-1])
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
@@ -183,6 +201,7 @@ def run_ours(args):
     from lidog_b200.lidog import synth, model as M, step
     from lidog_b200 import me as ME
     from lidog_b200.me import conv as meconv
+    from lidog_b200.me import norm as menorm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,9 +302,15 @@ def run_ours(args):
     if "k_gemm_tc" in by_kind:
         g = by_kind["k_gemm_tc"]
         ach = g["flops"] / (g["ms"] / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "k_gemm_tc (tcgen05 gather-GEMM, sparse-conv fwd+dgrad)",
+        traffic, traffic_src = ncu_traffic()
+        roofline = {"bound": "tensor", "kernel": "k_gemm2 (tcgen05 gather-GEMM, sparse-conv fwd+dgrad)",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                    "traffic": traffic,
+                    "traffic_note": None if traffic is None else
+                    f"dram read+write bytes of ONE launch of the block8 layer shape (ts 1, 96->96, 648k voxels) from "
+                    f"profiles/{traffic_src}; its algorithmic bytes are 124 MB fp16 operand + 249 MB fp32 result + "
+                    f"70 MB neighbour table; achieved/launches/avg_launch_ms aggregate all 122 launches of a step",
+                    "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                     "launches": g["n"], "avg_launch_ms": g["ms"] / g["n"],
                     "share_of_step": g["ms"] / total_ms,
                     "algorithmic_flops_per_step": g["flops"] / args.steps}
@@ -321,7 +346,9 @@ def run_ours(args):
                            "points_per_step_per_gpu": n_points, "global_batch": world * args.batch,
                            "parallelism": f"dp{world}" + (" (DDP + SyncBN over NCCL)" if world > 1 else ""),
                            "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",
-                           "conv_operands": meconv.CONFIG["tc"], "gather": {0: "cp.async v1", 1: "tma_gather4 v1", 2: "cp.async+mbarrier super-tile v2"}[meconv.CONFIG["gather"]]},
+                           "conv_operands": meconv.CONFIG["tc"], "gather": {0: "cp.async v1", 1: "tma_gather4 v1", 2: "cp.async+mbarrier super-tile v3, mask-sorted plans"}[meconv.CONFIG["gather"]],
+                           "fused_bn": bool(menorm.CONFIG["fused"]),
+                           "bev_layout": "channels_last" if lbev.CONFIG["channels_last"] else "nchw"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "sparse_conv_ms_per_scan": conv_ms / args.batch, "kernels": kernels,
                 "cpu_baseline": cpu}
