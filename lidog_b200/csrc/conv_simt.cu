@@ -188,20 +188,36 @@ __global__ void __launch_bounds__(128)
     float acc[C1_N];
 #pragma unroll
     for (int j = 0; j < C1_N; ++j) acc[j] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const uint32_t m = __ldg(plan.tile_mask + tile * plan.mask_words + (k >> 5));
-      if (!((m >> (k & 31)) & 1u)) continue;
-      const int nb = __ldg(plan.nbr + (int64_t)k * plan.k_stride + s);
-      if (nb >= 0) {
-        const float x = __ldg(X + nb);
-        const float4* w4 = reinterpret_cast<const float4*>(Ws + k * C1_N);
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int j = 0; j < C1_N / 4; ++j) {
-          const float4 w = w4[j];
-          acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+    for (int i = 0; i < 4; ++i)
+      if (i < plan.mask_words) mw[i] = __ldg(plan.tile_mask + tile * plan.mask_words + i);
+    // 8 offsets per round: the 8 neighbour ids, then the 8 gathered scalars, are independent loads in flight
+    // together (the k-at-a-time loop was a chain of 2 * 125 dependent global latencies per row)
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      const int wi = k0 >> 5;  // k0 is a multiple of 8: the 8 bits never straddle a word
+      const uint32_t word = wi == 0 ? mw[0] : wi == 1 ? mw[1] : wi == 2 ? mw[2] : mw[3];
+      const uint32_t bits = (word >> (k0 & 31)) & 0xffu;
+      if (!bits) continue;
+      int nb[8];
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        nb[j] = ((bits >> j) & 1u) ? __ldg(plan.nbr + (int64_t)(k0 + j) * plan.k_stride + s) : -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = nb[j] >= 0 ? __ldg(X + nb[j]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (nb[j] >= 0) {
+          const float4* w4 = reinterpret_cast<const float4*>(Ws + (k0 + j) * C1_N);
+#pragma unroll
+          for (int q = 0; q < C1_N / 4; ++q) {
+            const float4 w = w4[q];
+            acc[4 * q + 0] = fmaf(x[j], w.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x[j], w.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x[j], w.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x[j], w.w, acc[4 * q + 3]);
+          }
         }
       }
     }
@@ -222,11 +238,12 @@ __global__ void __launch_bounds__(128)
 // dW[k][co] = sum_o x[nbr[k][o]] * dY[o][co]: lane = output channel, acc[k] in registers, the gathered
 // scalars of a 32-row window staged in shared memory; one partial [K][32] per CTA, reduced in fixed order.
 constexpr int C1_KMAX = 128;
+constexpr int C1_XPITCH = C1_KMAX + 4;  // row pitch of the staged scalars: 16-byte aligned rows, 4-way instead of 32-way store conflicts
 
 __global__ void __launch_bounds__(256, 1)
     k_conv_c1_wgrad(lgConvPlan plan, const float* __restrict__ X, const float* __restrict__ dY,
                     float* __restrict__ partial) {
-  __shared__ __align__(16) float xs[32][C1_KMAX];
+  __shared__ __align__(16) float xs[32][C1_XPITCH];
   __shared__ float red[C1_KMAX][C1_N];
   const int K = plan.kernel_volume;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,23 +254,37 @@ __global__ void __launch_bounds__(256, 1)
   for (int64_t win = blockIdx.x; win < n_win; win += gridDim.x) {
     const int64_t s0 = win * 32;
     __syncthreads();
-    for (int e = threadIdx.x; e < C1_KMAX * 32; e += 256) {
-      const int k = e >> 5, r = e & 31;
-      float v = 0.f;
-      if (k < K) {
-        const int nb = __ldg(plan.nbr + (int64_t)k * plan.k_stride + s0 + r);
-        if (nb >= 0) v = __ldg(X + nb);
+    {  // stage x[nbr[k][s0 + r]] for the 32 rows of the window: all 16 id loads, then all 16 gathers, in flight together
+      constexpr int kPer = C1_KMAX * 32 / 256;
+      int nb[kPer];
+      float v[kPer];
+#pragma unroll
+      for (int it = 0; it < kPer; ++it) {
+        const int k = (threadIdx.x >> 5) + 8 * it;
+        nb[it] = (k < K) ? __ldg(plan.nbr + (int64_t)k * plan.k_stride + s0 + lane) : -1;
       }
-      xs[r][k] = v;
+#pragma unroll
+      for (int it = 0; it < kPer; ++it) v[it] = nb[it] >= 0 ? __ldg(X + nb[it]) : 0.f;
+#pragma unroll
+      for (int it = 0; it < kPer; ++it) xs[lane][(threadIdx.x >> 5) + 8 * it] = v[it];
     }
+    // the warp's 4 rows of the window: row ids and dY values loaded up front
+    int64_t rows[4];
+    float dys[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t s = s0 + warp + 8 * q;
+      rows[q] = plan.out_row ? (int64_t)__ldg(plan.out_row + s) : s;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dys[q] = (rows[q] >= 0 && rows[q] < plan.n_out) ? __ldg(dY + rows[q] * C1_N + lane) : 0.f;
     __syncthreads();
-#pragma unroll 1
-    for (int r = warp; r < 32; r += 8) {
-      const int64_t s = s0 + r;
-      int64_t row = plan.out_row ? (int64_t)plan.out_row[s] : s;
-      if (row < 0 || row >= plan.n_out) continue;
-      const float dy = __ldg(dY + row * C1_N + lane);
-      const float4* x4 = reinterpret_cast<const float4*>(&xs[r][0]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (rows[q] < 0 || rows[q] >= plan.n_out) continue;
+      const float dy = dys[q];
+      const float4* x4 = reinterpret_cast<const float4*>(&xs[warp + 8 * q][0]);
 #pragma unroll
       for (int j = 0; j < C1_KMAX / 4; ++j) {
         const float4 x = x4[j];
@@ -275,6 +306,152 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   float* P = partial + (int64_t)blockIdx.x * K * C1_N;
   for (int e = threadIdx.x; e < K * C1_N; e += 256) P[e] = red[e >> 5][e & 31];
+}
+
+// ------------------------------------------------------------------------------------ narrow head (K = 1)
+// `final` of MinkUNet34 (utils/models/minkunet_bev.py:118-123: kernel 1, 96 -> num_classes with bias) is a
+// plain [rows x C] x [C x n] product with n <= 8: one HBM pass over the wide matrix, nothing else.  The generic
+// 64-column tile kernels above spent 9x the arithmetic and staged everything through shared memory; these three
+// read / write the wide matrix once, coalesced (8 lanes per 128 bytes of a row).
+constexpr int HD_N = 8;      // padded narrow width
+constexpr int HD_CMAX = 256; // widest wide matrix
+
+// Y[s][0..n) = A[nbr[s]][:] @ W (C x n, row-major, n <= 8) + bias.  8 lanes per row, 4 rows per warp.
+__global__ void __launch_bounds__(256)
+    k_head_fwd(lgConvPlan plan, const float* __restrict__ A, int C, const float* __restrict__ W, int n,
+               const float* __restrict__ bias, float* __restrict__ Y) {
+  __shared__ __align__(16) float Ws[HD_CMAX][HD_N];
+  for (int e = threadIdx.x; e < C * HD_N; e += 256) {
+    const int c = e / HD_N, j = e % HD_N;
+    Ws[c][j] = j < n ? W[c * n + j] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l8 = lane & 7;
+  const int64_t rows_per_blk = 32 * 4;  // 8 warps x 4 rows x 4 rounds
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_blk; base < plan.n_out; base += (int64_t)gridDim.x * rows_per_blk) {
+#pragma unroll
+    for (int rnd = 0; rnd < 4; ++rnd) {
+      const int64_t s = base + rnd * 32 + (threadIdx.x >> 3);
+      const bool live = s < plan.n_out;
+      const int row = live ? __ldg(plan.nbr + s) : -1;
+      float acc[HD_N];
+#pragma unroll
+      for (int j = 0; j < HD_N; ++j) acc[j] = 0.f;
+      if (row >= 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(A + (int64_t)row * C);
+        for (int c4 = l8; c4 < C / 4; c4 += 8) {
+          const float4 a = __ldg(a4 + c4);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][4]);
+            acc[0] = fmaf(av[i], w0.x, acc[0]); acc[1] = fmaf(av[i], w0.y, acc[1]);
+            acc[2] = fmaf(av[i], w0.z, acc[2]); acc[3] = fmaf(av[i], w0.w, acc[3]);
+            acc[4] = fmaf(av[i], w1.x, acc[4]); acc[5] = fmaf(av[i], w1.y, acc[5]);
+            acc[6] = fmaf(av[i], w1.z, acc[6]); acc[7] = fmaf(av[i], w1.w, acc[7]);
+          }
+        }
+      }
+      // fixed-order butterfly over the 8 lanes of the row (every lane ends with the same sums)
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+        for (int j = 0; j < HD_N; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+      float mine = 0.f;
+#pragma unroll
+      for (int j = 0; j < HD_N; ++j) mine = (l8 == j) ? acc[j] : mine;
+      if (live && l8 < n) Y[s * n + l8] = mine + (bias ? bias[l8] : 0.f);
+    }
+  }
+}
+
+// dX[s][0..C) = dY[nbr[s]][0..n) @ W^T, W stored (C x n) row-major.  8 lanes per row, float4 stores.
+__global__ void __launch_bounds__(256)
+    k_head_dgrad(lgConvPlan plan, const float* __restrict__ dY, int n, const float* __restrict__ W, int C,
+                 float* __restrict__ dX) {
+  __shared__ __align__(16) float Ws[HD_CMAX][HD_N];
+  for (int e = threadIdx.x; e < C * HD_N; e += 256) {
+    const int c = e / HD_N, j = e % HD_N;
+    Ws[c][j] = j < n ? W[c * n + j] : 0.f;
+  }
+  __syncthreads();
+  const int l8 = threadIdx.x & 7;
+  for (int64_t s = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3); s < plan.n_out; s += (int64_t)gridDim.x * 32) {
+    const int row = __ldg(plan.nbr + s);
+    float g[HD_N];
+#pragma unroll
+    for (int j = 0; j < HD_N; ++j) g[j] = (row >= 0 && j < n) ? __ldg(dY + (int64_t)row * n + j) : 0.f;
+    float4* o4 = reinterpret_cast<float4*>(dX + s * C);
+    for (int c4 = l8; c4 < C / 4; c4 += 8) {
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][4]);
+        float a = g[0] * w0.x;
+        a = fmaf(g[1], w0.y, a); a = fmaf(g[2], w0.z, a); a = fmaf(g[3], w0.w, a);
+        a = fmaf(g[4], w1.x, a); a = fmaf(g[5], w1.y, a); a = fmaf(g[6], w1.z, a); a = fmaf(g[7], w1.w, a);
+        o[i] = a;
+      }
+      o4[c4] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// partial[blk][c][0..n) = sum over the block's rows of X[nbr[s]][c] * dY[s][0..n): lane = channel (coalesced
+// 128-byte row segments), warp = (row stripe, 32-channel group); warps of a block are combined in a fixed order.
+constexpr int HD_WG_BLOCKS = 592;
+__global__ void __launch_bounds__(256)
+    k_head_wgrad(lgConvPlan plan, const float* __restrict__ X, int C, const float* __restrict__ dY, int n,
+                 float* __restrict__ partial) {
+  __shared__ float red[8][32][HD_N + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = C / 32;
+  const int64_t rows_per_blk = (plan.n_out + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_blk;
+  const int64_t r1 = r0 + rows_per_blk < plan.n_out ? r0 + rows_per_blk : plan.n_out;
+  for (int gch = 0; gch < groups; ++gch) {
+    float acc[HD_N];
+#pragma unroll
+    for (int j = 0; j < HD_N; ++j) acc[j] = 0.f;
+    for (int64_t s = r0 + warp; s < r1; s += 32) {  // 4 rows in flight per warp
+      float x[4], g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t su = s + 8 * u;
+        const int row = su < r1 ? __ldg(plan.nbr + su) : -1;
+        x[u] = row >= 0 ? __ldg(X + (int64_t)row * C + gch * 32 + lane) : 0.f;
+        g[u] = (su < r1 && lane < n) ? __ldg(dY + su * n + lane) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < HD_N; ++j) acc[j] = fmaf(x[u], __shfl_sync(0xffffffffu, g[u], j), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < HD_N; ++j) red[warp][lane][j] = acc[j];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int j = 0; j < HD_N; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane][j];
+        if (j < n) partial[((int64_t)blockIdx.x * C + gch * 32 + lane) * n + j] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static bool head_shape(const lgConvPlan* plan, int wide, int narrow) {
+  return plan->kernel_volume == 1 && plan->out_row == nullptr && narrow >= 1 && narrow <= HD_N && wide % 32 == 0 &&
+         wide >= 32 && wide <= HD_CMAX && plan->n_out > 0;
+}
+static int head_wgrad_blocks(const lgConvPlan* plan) {
+  const int64_t want = ceil_div(plan->n_out, (int64_t)256);
+  return (int)(want < HD_WG_BLOCKS ? (want > 0 ? want : 1) : HD_WG_BLOCKS);
 }
 
 static int c1_wgrad_blocks(const lgConvPlan* plan) {
@@ -330,6 +507,18 @@ extern "C" int lg_conv_gemm_simt(const lgConvPlan* plan, const float* A, int32_t
     LG_LAUNCH_OK();
     return LG_OK;
   }
+  if (!w_transposed && head_shape(plan, Ca, N)) {  // 96 -> 7 head, forward
+    const int64_t want = ceil_div(plan->n_out, (int64_t)128);
+    k_head_fwd<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, (cudaStream_t)stream>>>(*plan, A, Ca, W, N, bias, Y);
+    LG_LAUNCH_OK();
+    return LG_OK;
+  }
+  if (w_transposed && !bias && head_shape(plan, N, Ca)) {  // its dgrad: 7 -> 96 through W^T
+    const int64_t want = ceil_div(plan->n_out, (int64_t)32);
+    k_head_dgrad<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, (cudaStream_t)stream>>>(*plan, A, Ca, W, N, Y);
+    LG_LAUNCH_OK();
+    return LG_OK;
+  }
   dim3 grid((unsigned)(plan->n_slots / TM), (unsigned)ceil_div(N, TN));
   k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(*plan, A, Ca, W, N, w_transposed, flip_k, bias, Y);
   LG_LAUNCH_OK();
@@ -341,6 +530,7 @@ extern "C" size_t lg_conv_wgrad_workspace(const lgConvPlan* plan, int32_t Ca, in
   int tpc;
   int chunks = wgrad_chunks(plan, &tpc);
   if (Ca == 1 && Cb == C1_N && chunks < c1_wgrad_blocks(plan)) chunks = c1_wgrad_blocks(plan);
+  if (head_shape(plan, Ca, Cb) && chunks < head_wgrad_blocks(plan)) chunks = head_wgrad_blocks(plan);
   return (size_t)chunks * plan->kernel_volume * Ca * Cb * sizeof(float) + 256;
 }
 
@@ -360,6 +550,12 @@ extern "C" int lg_conv_wgrad_simt(const lgConvPlan* plan, const float* X_in, int
   if (Cin == 1 && Cout == C1_N && plan->kernel_volume <= C1_KMAX) {
     const int blocks = c1_wgrad_blocks(plan);
     k_conv_c1_wgrad<<<blocks, 256, 0, stream>>>(*plan, X_in, dY_out, (float*)workspace);
+    LG_LAUNCH_OK();
+    return launch_reduce_partials((const float*)workspace, blocks, n_elems, nullptr, dW, stream);
+  }
+  if (head_shape(plan, Cin, Cout)) {
+    const int blocks = head_wgrad_blocks(plan);
+    k_head_wgrad<<<blocks, 256, 0, stream>>>(*plan, X_in, Cin, dY_out, Cout, (float*)workspace);
     LG_LAUNCH_OK();
     return launch_reduce_partials((const float*)workspace, blocks, n_elems, nullptr, dW, stream);
   }

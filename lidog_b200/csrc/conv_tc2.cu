@@ -50,6 +50,7 @@ constexpr int kIdxWarp = kProdWarp0 + kProdWarps;  // warp 10: row-id ring (bulk
 constexpr int kThreads = (kIdxWarp + 1) * 32;
 constexpr int kIdxSlotBytes = LG_TILE_ROWS * 4;
 constexpr int kSchedSlots = 4;                                   // super-tile hand-out ring
+constexpr int kSchedWords = 12;  // ring entry: [0] super-tile, [1] "tile has any offset" bits, [2..9] mask word 0 of its tiles
 constexpr int kSchedConsumers = kEpiWarps + 2 + kProdWarps;      // warps that read every ring entry
 constexpr int kStgPitch = 36;                                    // floats per staged row (32 + 4: conflict-free v4)
 constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;        // epilogue transposition buffers
@@ -80,25 +81,34 @@ struct SchedCursor {
   int slot;
   uint32_t phase;
 };
-__device__ __forceinline__ int64_t sched_next(SchedCursor& c, uint64_t* fullS, uint64_t* emptyS, const int* ring,
-                                              int lane, int* err) {
+// tile-mask words of the (<= 8) tiles of a super-tile, kept in registers; word 0 travels with the ring entry
+// (every layer on the tensor-core path has K <= 27 offsets = one word), further words are reloaded every 32 offsets
+struct TileMasks {
+  uint32_t w[8];
+};
+struct SchedItem {
+  int64_t st;    // super-tile index, < 0 = no more work
+  uint32_t any;  // bit t = tile t has at least one offset
+  TileMasks tm;  // mask word 0 of the tiles
+};
+// All helpers below are called by fully active warps and broadcast lane 0's value, so everything derived from
+// them (unit sequence, stage counters, descriptors) is warp-uniform for ptxas.
+__device__ __forceinline__ void sched_next(SchedItem& it, SchedCursor& c, uint64_t* fullS, uint64_t* emptyS,
+                                           const int* ring, int lane, int* err) {
   mbar_wait(&fullS[c.slot], c.phase, err, 20);
-  const int st = (int)bcast0((uint32_t) * (const volatile int*)(ring + c.slot));
+  const volatile int* e = ring + c.slot * kSchedWords;
+  it.st = (int)bcast0((uint32_t)e[0]);
+  it.any = bcast0((uint32_t)e[1]);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) it.tm.w[t] = bcast0((uint32_t)e[2 + t]);
   __syncwarp();
   if (lane == 0) mbar_arrive(&emptyS[c.slot]);
   if (++c.slot == kSchedSlots) {
     c.slot = 0;
     c.phase ^= 1;
   }
-  return st;
 }
 
-// tile-mask words of the (<= 8) tiles of a super-tile, kept in registers; reloaded every 32 offsets
-struct TileMasks {
-  uint32_t w[8];
-};
-// All mask helpers are called by fully active warps and broadcast lane 0's value, so everything derived
-// from them (unit sequence, stage counters, descriptors) is warp-uniform for ptxas.
 __device__ __forceinline__ void load_masks(TileMasks& tm, const lgConvPlan& p, int64_t tile0, int nt, int word) {
 #pragma unroll
   for (int t = 0; t < 8; ++t)
@@ -168,6 +178,7 @@ struct Gemm2Args {
   int Ck, N, n_blk, flip, umma_fmt;
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
+  int bmax;                         // units the MMA warp waits for together (one proxy fence per batch), <= sa
   int sets;                         // accumulator sets in TMEM (sets * T * n_blk <= 512): 2 = the epilogue of one
                                     // super-tile overlaps the MMAs of the next
   int64_t n_tiles, n_super;
@@ -243,21 +254,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       if (lane == 0) drawn = atomicAdd(g.sched + blockIdx.y, 1);
       drawn = (int)bcast0((uint32_t)drawn);
       const int64_t st = drawn < g.n_super ? g.n_super - 1 - drawn : -1;
+      const int64_t tile0 = st * g.T;
+      const int nt = st < 0 ? 0 : (int)min((int64_t)g.T, g.n_tiles - tile0);
+      // the entry carries the tiles' mask words, so the other nine warps never go to global memory for them
+      uint32_t w0 = 0;
+      if (lane < nt) w0 = __ldg(g.plan.tile_mask + (tile0 + lane) * g.plan.mask_words);
+      uint32_t any = __ballot_sync(0xffffffffu, w0 != 0);
+      if (g.plan.mask_words > 1 && st >= 0) any = any_mask(g.plan, tile0, nt);
+      int* entry = sched_ring + sc.slot * kSchedWords;
+      if (lane < 8) entry[2 + lane] = (int)w0;
       if (lane == 0) {
-        sched_ring[sc.slot] = (int)st;
-        mbar_arrive(&fullS[sc.slot]);
+        entry[0] = (int)st;
+        entry[1] = (int)any;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&fullS[sc.slot]);
       __syncwarp();
       if (++sc.slot == kSchedSlots) {
         sc.slot = 0;
         sc.phase ^= 1;
       }
       if (st < 0) break;
-      const int64_t tile0 = st * g.T;
-      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks tm;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) tm.w[t] = __shfl_sync(0xffffffffu, w0, t);
       for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
         const uint32_t m = present_bits(tm, k);
         if (!m) continue;
         for (int p = 0; p < g.n_panels; ++p) {
@@ -284,14 +306,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     const int pw = warp - kProdWarp0;
     int stage = 0, turn = 0, slot = 0;
     uint32_t phase = 0, iphase = 0;
+    SchedItem item;
     for (;;) {
-      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      sched_next(item, sc, fullS, emptyS, sched_ring, lane, g.err);
+      const int64_t st = item.st;
       if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-      TileMasks tm;
+      TileMasks& tm = item.tm;
       for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
         const uint32_t m = present_bits(tm, k);
         if (!m) continue;
         for (int p = 0; p < g.n_panels; ++p) {
@@ -331,14 +355,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== B producer (weight panels, TMA)
     int bs = 0;
     uint32_t bphase = 0;
+    SchedItem item;
     for (;;) {
-      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      sched_next(item, sc, fullS, emptyS, sched_ring, lane, g.err);
+      const int64_t st = item.st;
       if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-      TileMasks tm;
+      TileMasks& tm = item.tm;
       for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
         if (!present_bits(tm, k)) continue;
         const int wk = g.flip ? (K - 1 - k) : k;
         for (int p = 0; p < g.n_panels; ++p) {
@@ -378,59 +404,91 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     const int pc = g.pc;
     int stage = 0, bs = 0;
     uint32_t phase = 0, bphase = 0, it = 0;
+    SchedItem item;
     for (;;) {
-      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      PROF_T0();
+      sched_next(item, sc, fullS, emptyS, sched_ring, lane, g.err);
+      const int64_t st = item.st;
       if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-      if (!any_mask(g.plan, tile0, nt)) continue;
+      if (!item.any) continue;
       const int set = (g.sets == 2) ? (int)(it & 1) : 0;
       const uint32_t eparity = (((g.sets == 2) ? (it >> 1) : it) & 1) ^ 1;
       const int a0 = set * g.T;  // first accumulator of this set
       ++it;
       uint32_t started = 0;
-      TileMasks tm;
+      TileMasks& tm = item.tm;
+      PROF_ADD(11);
       for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0) load_masks(tm, g.plan, tile0, nt, k >> 5);
+        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
         const uint32_t m = present_bits(tm, k);
         if (!m) continue;
         for (int p = 0; p < g.n_panels; ++p) {
-          PROF_T0();
+          PROF_ADD(7);
           mbar_wait(&fullB[bs], bphase, g.err, 4);
           PROF_ADD(4);
           const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
-          for (uint32_t mm = m; mm; mm &= mm - 1) {
-            const int t = __ffs(mm) - 1;
-            PROF_ADD(7);
-            if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
-            PROF_ADD(3);
-            mbar_wait(&fullA[stage], phase, g.err, 5);
+          // The units of this (offset, panel) are taken in batches of <= bmax (<= ring depth): wait for all their
+          // stages, ONE proxy fence, then issue them back to back -- the fence and the barrier round trips are
+          // paid per batch instead of per unit.
+          uint32_t mm = m;
+          while (mm) {
+            uint32_t batch = 0;
+            {
+              uint32_t x = mm;
+              for (int i = 0; i < g.bmax && x; ++i) {
+                batch |= x & (0u - x);
+                x &= x - 1;
+              }
+            }
+            mm &= ~batch;
+            {
+              int s = stage;
+              uint32_t ph = phase;
+              for (uint32_t bb = batch; bb; bb &= bb - 1) {
+                const int t = __ffs(bb) - 1;
+                if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
+                mbar_wait(&fullA[s], ph, g.err, 5);
+                if (++s == g.sa) {
+                  s = 0;
+                  ph ^= 1;
+                }
+              }
+            }
             PROF_ADD(5);
             if (!(g.dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
             tc_fence_after();
             PROF_ADD(10);
-            const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
-            const uint32_t d_tmem = tmem_base + (a0 + t) * g.n_blk;
-            const uint32_t acc0 = (started >> t) & 1u;
             if (elect_one()) {
-              if (!(g.dbg & 4)) {
+              int s = stage;
+              for (uint32_t bb = batch; bb; bb &= bb - 1) {
+                const int t = __ffs(bb) - 1;
+                const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
+                const uint32_t d_tmem = tmem_base + (a0 + t) * g.n_blk;
+                const uint32_t acc0 = (started >> t) & 1u;
+                if (!(g.dbg & 4)) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  if (c < pc) {
-                    umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, c == 0 ? acc0 : 1u);
-                    umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
+                  for (int c = 0; c < 4; ++c) {
+                    if (c < pc) {
+                      umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, c == 0 ? acc0 : 1u);
+                      umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
+                    }
                   }
                 }
+                umma_commit(&emptyA[s]);
+                if (++s == g.sa) s = 0;
               }
-              umma_commit(&emptyA[stage]);
             }
             __syncwarp();
             PROF_ADD(6);
-            started |= 1u << t;
-            pacc[13] += 1;  // units
-            if (++stage == g.sa) {
-              stage = 0;
-              phase ^= 1;
+            started |= batch;
+            for (int i = __popc(batch); i > 0; --i) {
+              pacc[13] += 1;  // units
+              if (++stage == g.sa) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
           if (elect_one()) umma_commit(&emptyB[bs]);
@@ -447,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
         if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
       if (elect_one()) umma_commit(&acc_full[set]);
       __syncwarp();
+      PROF_ADD(3);
       pacc[14] += 1;  // super-tiles
     }
     pacc[12] = clock64() - cta_t0;  // lifetime of the MMA role of this CTA
@@ -454,12 +513,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== epilogue (warps 0..3)
     const float scale = g.out_scale ? g.out_scale[0] : 1.f;
     uint32_t it = 0;
+    SchedItem item;
     for (;;) {
-      const int64_t st = sched_next(sc, fullS, emptyS, sched_ring, lane, g.err);
+      sched_next(item, sc, fullS, emptyS, sched_ring, lane, g.err);
+      const int64_t st = item.st;
       if (st < 0) break;
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
-      const uint32_t am = any_mask(g.plan, tile0, nt);
+      const uint32_t am = item.any;
       PROF_T0();
       int a0 = 0;
       if (am) {
@@ -553,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   if (warp == kProdWarp0) PROF_FLUSH(0, 1);
   if (warp == kBWarp) PROF_FLUSH(2, 2);
   if (warp == kMmaWarp) PROF_FLUSH(3, 7);
-  if (warp == kMmaWarp) PROF_FLUSH(10, 14);
+  if (warp == kMmaWarp) PROF_FLUSH(10, 14);  // 11 = schedule hand-out + super-tile prologue of the MMA warp
   if (warp == 0) PROF_FLUSH(8, 9);
   tc_fence_before();
   __syncthreads();
@@ -811,7 +872,7 @@ static inline size_t wgrad_tail_bytes(int sa, int sb) {  // id ring + barriers +
 static inline size_t tail_bytes(int sa, int sb) {  // + epilogue staging + schedule ring
   const int ni = 8 * kProdWarps;
   return (size_t)ni * kIdxSlotBytes + kStgBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 11 + 2 * kSchedSlots) * 8 + 16 +
-         4 * kSchedSlots + 1024;
+         4 * kSchedWords * kSchedSlots + 1024;
 }
 
 }  // namespace v2
@@ -895,10 +956,37 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   }
   g.T = T;
   g.n_super = ceil_div(g.n_tiles, T);
+  // Pipeline shape.  The weight-panel ring gets 3 stages whenever 4 operand stages still fit next to it (with 2,
+  // the TMA load of the next panel cannot start before the MMAs of the current one retire: the 256-channel
+  // layers waited 22 % of the time for weights); the rest of the budget goes to operand (gather) stages.
+  // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments.
+  int opt = 3;
+  {
+    const char* e = getenv("LIDOG_G2_OPT");
+    if (e) opt = atoi(e);
+  }
+  int force_sb = 0, force_pc = 0;
+  {
+    const char* e = getenv("LIDOG_G2_SB");
+    if (e) force_sb = atoi(e);
+    e = getenv("LIDOG_G2_PC");
+    if (e) force_pc = atoi(e);
+  }
+  if (force_pc > 0 && force_pc < g.pc) {
+    int pc = force_pc;
+    while (n_chunks % pc != 0) --pc;
+    g.pc = pc;
+    g.n_panels = n_chunks / pc;
+  }
   size_t stageA, stageB;
   for (;;) {
     stageA = (size_t)g.pc * kSub, stageB = (size_t)g.pc * g.n_blk * kRowB;
-    g.sb = (3 * stageB <= 80 * 1024) ? 3 : 2;
+    if (force_sb >= 2)
+      g.sb = force_sb;
+    else if (opt & 2)
+      g.sb = (3 * stageB + 4 * stageA + tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
+    else
+      g.sb = (3 * stageB <= 80 * 1024) ? 3 : 2;
     g.sa = 12;
     while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
     if (g.sa >= kProdWarps || g.pc == 1) break;
@@ -908,6 +996,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     g.pc = pc;
     g.n_panels = n_chunks / pc;
   }
+  g.bmax = (opt & 1) ? (g.sa < 4 ? g.sa : 4) : 1;
   // Ring-phase rule: a producer warp revisits a stage only after the consumer freed it once, which the
   // parity wait can tell only when consecutive units of one warp are < one ring wrap apart: np <= sa.
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
@@ -936,7 +1025,14 @@ static int wgrad2_shape(const lgConvPlan* plan, int Cin, int Cout, int* G, int* 
   *G = (K + *n_groups - 1) / *n_groups;
   const int m_blocks = (Cin + 127) / 128;
   const int64_t n_tiles = plan->n_slots / LG_TILE_ROWS;
-  int64_t want = 592 / ((int64_t)*n_groups * m_blocks);
+  // CTAs per launch: 4 waves of 148 by default; every chunk costs one partial dW (written, then re-read by the
+  // reduction), so small layers pay for many chunks.  LIDOG_WG_CTAS overrides the target for experiments.
+  static int target_ctas = 0;
+  if (!target_ctas) {
+    const char* e = getenv("LIDOG_WG_CTAS");
+    target_ctas = e && atoi(e) > 0 ? atoi(e) : 592;
+  }
+  int64_t want = target_ctas / ((int64_t)*n_groups * m_blocks);
   if (want < 1) want = 1;
   int64_t chunks = n_tiles < want ? n_tiles : want;
   if (chunks < 1) chunks = 1;

@@ -82,7 +82,10 @@ def _run_case(cuda, mode, kind, ts_in, ksize, cin, cout, bias, tol, seed=0, sort
 
 SIMT_CASES = [
     ("same", 1, 5, 1, 32, False),    # stem conv0p1s1
-    ("identity", 1, 1, 96, 7, True),  # class head with bias
+    ("identity", 1, 1, 96, 7, True),  # class head with bias (narrow-head kernels, csrc/conv_simt.cu)
+    ("identity", 1, 1, 256, 3, False),  # narrow head, widest operand, no bias
+    ("identity", 2, 1, 32, 8, True),    # narrow head, full 8 columns
+    ("identity", 1, 1, 96, 19, True),  # 19-class head (BASELINE configs[0]): generic tile kernel
     ("same", 1, 3, 32, 32, False),
     ("same", 2, 3, 32, 64, False),
     ("down", 1, 2, 32, 32, False),

@@ -37,6 +37,9 @@ CASES_ALL = [
     ("same", 16, 3, 256, 256), ("down", 1, 2, 32, 32), ("up", 2, 2, 96, 96), ("identity", 1, 1, 128, 96),
 ]
 CASES_TOP = [("same", 1, 3, 96, 96), ("same", 2, 3, 64, 64), ("same", 8, 3, 256, 256)]
+# the 3x3x3 layer shapes MinkUNet34 actually runs (Appendix A of SURVEY.md), one per (stride, width)
+CASES_NET = [("same", 16, 3, 256, 256), ("same", 8, 3, 256, 256), ("same", 8, 3, 128, 128), ("same", 4, 3, 128, 128),
+             ("same", 4, 3, 64, 64), ("same", 2, 3, 96, 96), ("same", 2, 3, 32, 32), ("same", 1, 3, 96, 96)]
 
 
 def main():
@@ -70,7 +73,7 @@ def main():
     only = args.only.split(",")
     for srt in [int(v) for v in args.sorted.split(",")]:
       meconv.CONFIG["sorted"] = srt
-      for kind, ts, ks, cin, cout in (CASES_ALL if args.cases == "all" else CASES_TOP):
+      for kind, ts, ks, cin, cout in {"all": CASES_ALL, "top": CASES_TOP, "net": CASES_NET}[args.cases]:
           if srt == 1 and kind in ("up", "identity") and "0" in args.sorted.split(","):
               continue  # these plans have no sorted variant
           cls = ME.MinkowskiConvolutionTranspose if kind == "up" else ME.MinkowskiConvolution
