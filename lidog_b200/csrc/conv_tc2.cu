@@ -64,6 +64,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address: fire and forget
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ int lds32(uint32_t saddr) {
   int v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
@@ -120,6 +124,19 @@ __device__ __forceinline__ uint32_t present_bits(const TileMasks& tm, int k) {
   for (int t = 0; t < 8; ++t) m |= ((tm.w[t] >> (k & 31)) & 1u) << t;
   return m;
 }
+// offsets present in ANY tile of the super-tile, for mask word `word` (word 0 came with the ring entry)
+__device__ __forceinline__ uint32_t offset_bits(TileMasks& tm, const lgConvPlan& p, int64_t tile0, int nt, int word) {
+  if (word) load_masks(tm, p, tile0, nt, word);
+  return ((tm.w[0] | tm.w[1]) | (tm.w[2] | tm.w[3])) | ((tm.w[4] | tm.w[5]) | (tm.w[6] | tm.w[7]));
+}
+// Every role walks the same (offset k, tile bits m) sequence: set bits only -- the one-thread roles used to spend
+// ~100 cycles per ABSENT offset on the shift/or chains of a plain k = 0..K-1 scan.
+#define LG_FOR_EACH_OFFSET(tm, plan, tile0, nt, k, m)                                                  \
+  for (int _w = 0; _w < (plan).mask_words; ++_w)                                                       \
+    for (uint32_t _kb = offset_bits(tm, plan, tile0, nt, _w); _kb; _kb &= _kb - 1)                     \
+      if (const int k = 32 * _w + __ffs(_kb) - 1; true)                                                \
+        if (const uint32_t m = present_bits(tm, k); true)
+
 __device__ __forceinline__ uint32_t any_mask(const lgConvPlan& p, int64_t tile0, int nt) {
   uint32_t m = 0;
   for (int t = 0; t < nt; ++t) {
@@ -178,6 +195,7 @@ struct Gemm2Args {
   int Ck, N, n_blk, flip, umma_fmt;
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
+  int pf;                           // id warp prefetches the operand rows of upcoming units into L2
   int bmax;                         // units the MMA warp waits for together (one proxy fence per batch), <= sa
   int sets;                         // accumulator sets in TMEM (sets * T * n_blk <= 512): 2 = the epilogue of one
                                     // super-tile overlaps the MMAs of the next
@@ -248,6 +266,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== id ring (runs ahead; one elected lane issues)
     int slot = 0;
     uint32_t iphase = 0;
+    // L2 prefetch of the operand rows, kPfLag units behind the id copies (those ids have landed) and up to
+    // ni - kPfLag units ahead of the gathers: a first touch then costs the cp.async an L2 hit, not a DRAM trip
+    constexpr int kPfLag = 8;
+    int pslot = 0, pf_count = 0;
+    uint32_t pphase = 0, pf_hist = 0;
+    const uint32_t row_bytes = (uint32_t)g.Ck * 2u;
     for (;;) {
       mbar_wait(&emptyS[sc.slot], sc.phase ^ 1, g.err, 21);
       int drawn = 0;
@@ -278,10 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       TileMasks tm;
 #pragma unroll
       for (int t = 0; t < 8; ++t) tm.w[t] = __shfl_sync(0xffffffffu, w0, t);
-      for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
-        const uint32_t m = present_bits(tm, k);
-        if (!m) continue;
+      LG_FOR_EACH_OFFSET(tm, g.plan, tile0, nt, k, m) {
         for (int p = 0; p < g.n_panels; ++p) {
           for (uint32_t mm = m; mm; mm &= mm - 1) {
             const int t = __ffs(mm) - 1;
@@ -296,6 +317,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             if (++slot == ni) {
               slot = 0;
               iphase ^= 1;
+            }
+            if (g.pf) {
+              pf_hist = (pf_hist << 1) | (p == 0 ? 1u : 0u);  // later panels of a unit re-read the same rows
+              if (++pf_count > kPfLag) {
+                if ((pf_hist >> kPfLag) & 1u) {
+                  mbar_wait(&fullI[pslot], pphase, g.err, 9);
+                  const int4 ids = *reinterpret_cast<const int4*>(smI + (size_t)pslot * kIdxSlotBytes + lane * 16);
+                  const uint8_t* a = reinterpret_cast<const uint8_t*>(g.A);
+                  if (ids.x >= 0) bulk_prefetch_l2(a + (size_t)ids.x * row_bytes, row_bytes);
+                  if (ids.y >= 0) bulk_prefetch_l2(a + (size_t)ids.y * row_bytes, row_bytes);
+                  if (ids.z >= 0) bulk_prefetch_l2(a + (size_t)ids.z * row_bytes, row_bytes);
+                  if (ids.w >= 0) bulk_prefetch_l2(a + (size_t)ids.w * row_bytes, row_bytes);
+                }
+                if (++pslot == ni) {
+                  pslot = 0;
+                  pphase ^= 1;
+                }
+              }
             }
           }
         }
@@ -314,10 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks& tm = item.tm;
-      for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
-        const uint32_t m = present_bits(tm, k);
-        if (!m) continue;
+      LG_FOR_EACH_OFFSET(tm, g.plan, tile0, nt, k, m) {
         for (int p = 0; p < g.n_panels; ++p) {
           for (int t = 0; t < nt; ++t) {
             if (!((m >> t) & 1u)) continue;
@@ -363,9 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       const int64_t tile0 = st * g.T;
       const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
       TileMasks& tm = item.tm;
-      for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
-        if (!present_bits(tm, k)) continue;
+      LG_FOR_EACH_OFFSET(tm, g.plan, tile0, nt, k, m) {
+        (void)m;
         const int wk = g.flip ? (K - 1 - k) : k;
         for (int p = 0; p < g.n_panels; ++p) {
           PROF_T0();
@@ -420,10 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       uint32_t started = 0;
       TileMasks& tm = item.tm;
       PROF_ADD(11);
-      for (int k = 0; k < K; ++k) {
-        if ((k & 31) == 0 && k) load_masks(tm, g.plan, tile0, nt, k >> 5);
-        const uint32_t m = present_bits(tm, k);
-        if (!m) continue;
+      LG_FOR_EACH_OFFSET(tm, g.plan, tile0, nt, k, m) {
         for (int p = 0; p < g.n_panels; ++p) {
           PROF_ADD(7);
           mbar_wait(&fullB[bs], bphase, g.err, 4);
@@ -960,7 +992,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   // the TMA load of the next panel cannot start before the MMAs of the current one retire: the 256-channel
   // layers waited 22 % of the time for weights); the rest of the budget goes to operand (gather) stages.
   // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments.
-  int opt = 3;
+  int opt = 7;
   {
     const char* e = getenv("LIDOG_G2_OPT");
     if (e) opt = atoi(e);
@@ -997,6 +1029,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     g.n_panels = n_chunks / pc;
   }
   g.bmax = (opt & 1) ? (g.sa < 4 ? g.sa : 4) : 1;
+  g.pf = (opt & 4) ? 1 : 0;
   // Ring-phase rule: a producer warp revisits a stage only after the consumer freed it once, which the
   // parity wait can tell only when consecutive units of one warp are < one ring wrap apart: np <= sa.
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
@@ -1025,14 +1058,26 @@ static int wgrad2_shape(const lgConvPlan* plan, int Cin, int Cout, int* G, int* 
   *G = (K + *n_groups - 1) / *n_groups;
   const int m_blocks = (Cin + 127) / 128;
   const int64_t n_tiles = plan->n_slots / LG_TILE_ROWS;
-  // CTAs per launch: 4 waves of 148 by default; every chunk costs one partial dW (written, then re-read by the
-  // reduction), so small layers pay for many chunks.  LIDOG_WG_CTAS overrides the target for experiments.
-  static int target_ctas = 0;
-  if (!target_ctas) {
+  // Chunks of tiles per (offset group, channel block).  Every chunk costs one partial dW (written by the epilogue,
+  // re-read by the reduction) and one pipeline ramp, so a chunk should own >= ~32 tiles; but the launch wants at
+  // least one wave of 148 CTAs and gains nothing beyond four.  Measured (profiles/r01_s4_sweep_a.txt): the layers at
+  // tensor stride >= 4 ran 1.3-1.8x faster with 148 CTAs than with 592, the stride-1 layers 1.3x slower.
+  // LIDOG_WG_CTAS pins the CTA target for experiments.
+  static int target_ctas = -1;
+  if (target_ctas < 0) {
     const char* e = getenv("LIDOG_WG_CTAS");
-    target_ctas = e && atoi(e) > 0 ? atoi(e) : 592;
+    target_ctas = e && atoi(e) > 0 ? atoi(e) : 0;
   }
-  int64_t want = target_ctas / ((int64_t)*n_groups * m_blocks);
+  const int64_t per = (int64_t)*n_groups * m_blocks;
+  int64_t want;
+  if (target_ctas) {
+    want = target_ctas / per;
+  } else {
+    const int64_t hi = 592 / per, lo = ceil_div((int64_t)148, per);
+    want = n_tiles / 32;
+    if (want < lo) want = lo;
+    if (want > hi) want = hi;
+  }
   if (want < 1) want = 1;
   int64_t chunks = n_tiles < want ? n_tiles : want;
   if (chunks < 1) chunks = 1;
