@@ -233,26 +233,52 @@ __device__ __forceinline__ int64_t out_index(int layout, int b, int c, int i, in
   return layout ? (((int64_t)b * h_out + i) * w_out + j) * C + c : (((int64_t)b * C + c) * h_out + i) * w_out + j;
 }
 
-// staged tile <-> global, coalesced for the layout (NHWC: c' fastest, NCHW: j fastest)
+// staged tile <-> global, coalesced for the layout.  A warp moves one 32-element line per iteration (NHWC:
+// the 32 scrambled channels of one output pixel, NCHW: 32 columns of one (channel, row)), lane = position
+// in the line: one shared-memory access (pitch 33: conflict-free both ways), one global access and a handful
+// of integer instructions per element -- the flat-index form with its three divisions and 64-bit
+// multiplications per element cost as much as the pooling itself.
 template <bool STORE>
 __device__ __forceinline__ void tile_transfer(const TileGeom& g, float* s_out, float* gptr, int layout, int C, int h_out,
                                               int w_out, bool zero) {
   static_assert(kCG == 32 && kJC == 32 && kIB == 8, "index decomposition below assumes 32 x 8 x 32 tiles");
-  for (int e = threadIdx.x; e < kIB * kJC * kCG; e += blockDim.x) {
-    int cl, il, jl;
-    if (layout) {
-      cl = e & 31, jl = (e >> 5) & 31, il = e >> 10;
-    } else {
-      jl = e & 31, il = (e >> 5) & 7, cl = e >> 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (layout) {  // NHWC: line = (il, jl), lane = c'
+    if (lane >= g.ncg) return;
+    float* base = gptr + (((int64_t)g.b * h_out + g.i0) * w_out + g.j0) * C + g.c0 + lane;
+    for (int line = warp; line < kIB * kJC; line += nwarps) {
+      const int il = line >> 5, jl = line & 31;
+      if (il >= g.nib || jl >= g.njc) continue;
+      float* ge = base + ((int64_t)il * w_out + jl) * C;
+      float* se = s_out + (il * kJC + jl) * kPitch + lane;
+      if (STORE)
+        *ge = zero ? 0.f : *se;
+      else
+        *se = *ge;
     }
-    if (cl >= g.ncg || il >= g.nib || jl >= g.njc) continue;
-    const int se = (il * kJC + jl) * kPitch + cl;
-    const int64_t ge = out_index(layout, g.b, g.c0 + cl, g.i0 + il, g.j0 + jl, C, h_out, w_out);
-    if (STORE)
-      gptr[ge] = zero ? 0.f : s_out[se];
-    else
-      s_out[se] = gptr[ge];
+  } else {  // NCHW: line = (c', il), lane = jl
+    if (lane >= g.njc) return;
+    float* base = gptr + (((int64_t)g.b * C + g.c0) * h_out + g.i0) * w_out + g.j0 + lane;
+    for (int line = warp; line < kCG * kIB; line += nwarps) {
+      const int cl = line >> 3, il = line & 7;
+      if (cl >= g.ncg || il >= g.nib) continue;
+      float* ge = base + ((int64_t)cl * h_out + il) * w_out;
+      float* se = s_out + (il * kJC + lane) * kPitch + cl;
+      if (STORE)
+        *ge = zero ? 0.f : *se;
+      else
+        *se = *ge;
+    }
   }
+}
+
+// bit h - ha of the result: scrambled row h of window row i (channel c') holds a voxel; 0 = every window of this
+// (c', i) line pools zeros only.  Independent of the column, so a warp tests it once for its 32 windows.
+__device__ __forceinline__ uint32_t line_row_bits(const TileGeom& g, const TileSmem& t, int cl, int i, int H, int pk,
+                                                  int ps, int pp) {
+  const int h0 = i * ps - pp;
+  const int ha = max(h0, 0), hb = min(h0 + pk, H);
+  return (t.rowmask[cl] >> (ha - g.h_lo)) & ((1u << (hb - ha)) - 1u);
 }
 
 __global__ void __launch_bounds__(256)
@@ -273,7 +299,7 @@ __global__ void __launch_bounds__(256)
     const int cl = r >> 3, il = r & 7;
     if (cl >= g.ncg || il >= g.nib) continue;
     float v = 0.f;
-    if (lane < g.njc)
+    if (lane < g.njc && line_row_bits(g, t, cl, g.i0 + il, H, pk, ps, pp))  // warp-uniform: most lines are all zeros
       v = window_scan<false>(g, t, cl, g.i0 + il, g.j0 + lane, C, H, W, pk, ps, pp, max_pix, policy, feats, next,
                              nullptr, nullptr);
     t.out[(il * kJC + lane) * kPitch + cl] = v;
@@ -300,6 +326,7 @@ __global__ void __launch_bounds__(256)
   for (int r = warp; r < kCG * kIB; r += 8) {
     const int cl = r >> 3, il = r & 7, jl = lane;
     if (cl >= g.ncg || il >= g.nib || jl >= g.njc) continue;
+    if (!line_row_bits(g, t, cl, g.i0 + il, H, pk, ps, pp)) continue;  // warp-uniform: only empty zeros can win
     const float gv = t.out[(il * kJC + jl) * kPitch + cl];
     if (gv == 0.f) continue;
     int row = -1, ch = 0;

@@ -266,8 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // ===================================================================== id ring (runs ahead; one elected lane issues)
     int slot = 0;
     uint32_t iphase = 0;
-    // L2 prefetch of the operand rows, kPfLag units behind the id copies (those ids have landed) and up to
-    // ni - kPfLag units ahead of the gathers: a first touch then costs the cp.async an L2 hit, not a DRAM trip
+    // Optional (LIDOG_G2_OPT & 4, OFF by default): L2 prefetch of the operand rows, kPfLag units behind the id copies
+    // and up to ni - kPfLag units ahead of the gathers.  Measured on B200 (profiles/r01_s4_sweep_b.txt): 128
+    // cp.async.bulk.prefetch.L2 per unit made every layer 1.2-6x SLOWER (0.229 -> 0.834 ms on the block8 shape);
+    // the bulk-prefetch path serialises far below the rate the LDGSTS gathers sustain.  Kept as the record.
     constexpr int kPfLag = 8;
     int pslot = 0, pf_count = 0;
     uint32_t pphase = 0, pf_hist = 0;
@@ -670,7 +672,7 @@ struct Wgrad2Args {
   const uint16_t* X;
   const uint16_t* dY;
   float* partial;  // [chunks][K][Cin][Cout]
-  int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np;
+  int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np, bmax;
   int64_t n_tiles;
   int* err;
 };
@@ -823,26 +825,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
       if (!m) continue;
       mbar_wait(&fullB[bs], bphase, g.err, 13);
       const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
-      for (uint32_t mm = m; mm; mm &= mm - 1) {
-        const int j = __ffs(mm) - 1;
-        mbar_wait(&fullA[stage], phase, g.err, 14);
+      // the offsets of this tile in batches of <= bmax (<= ring depth): all waits, one proxy fence, then the MMAs
+      uint32_t mm = m;
+      while (mm) {
+        uint32_t batch = 0;
+        {
+          uint32_t x = mm;
+          for (int i = 0; i < g.bmax && x; ++i) {
+            batch |= x & (0u - x);
+            x &= x - 1;
+          }
+        }
+        mm &= ~batch;
+        {
+          int s = stage;
+          uint32_t ph = phase;
+          for (uint32_t bb = batch; bb; bb &= bb - 1) {
+            mbar_wait(&fullA[s], ph, g.err, 14);
+            if (++s == g.sa) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
         fence_proxy_async();
         tc_fence_after();
-        const uint64_t da0 = desc_hi | (uint64_t)(a_base + stage * a_stage16);
-        const uint32_t d_tmem = tmem_base + j * g.Cout;
-        const uint32_t acc0 = (started >> j) & 1u;
         if (elect_one()) {
-          umma_f16(d_tmem, da0, db0, idesc, acc0);
+          int s = stage;
+          for (uint32_t bb = batch; bb; bb &= bb - 1) {
+            const int j = __ffs(bb) - 1;
+            const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
+            const uint32_t d_tmem = tmem_base + j * g.Cout;
+            const uint32_t acc0 = (started >> j) & 1u;
+            umma_f16(d_tmem, da0, db0, idesc, acc0);
 #pragma unroll
-          for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
-            umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
-          umma_commit(&emptyA[stage]);
+            for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
+              umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
+            umma_commit(&emptyA[s]);
+            if (++s == g.sa) s = 0;
+          }
         }
         __syncwarp();
-        started |= 1u << j;
-        if (++stage == g.sa) {
-          stage = 0;
-          phase ^= 1;
+        started |= batch;
+        for (int i = __popc(batch); i > 0; --i) {
+          if (++stage == g.sa) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
       if (elect_one()) umma_commit(&emptyB[bs]);
@@ -991,8 +1020,9 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   // Pipeline shape.  The weight-panel ring gets 3 stages whenever 4 operand stages still fit next to it (with 2,
   // the TMA load of the next panel cannot start before the MMAs of the current one retire: the 256-channel
   // layers waited 22 % of the time for weights); the rest of the budget goes to operand (gather) stages.
-  // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments.
-  int opt = 7;
+  // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments;
+  // LIDOG_G2_OPT bits: 1 = batched waits of the MMA warp, 2 = deep panel ring, 4 = L2 row prefetch (see k_gemm2).
+  int opt = 3;
   {
     const char* e = getenv("LIDOG_G2_OPT");
     if (e) opt = atoi(e);
@@ -1115,6 +1145,11 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   g.sa = 5;
   while (g.sa > 2 && g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
+  {
+    const char* e = getenv("LIDOG_WG_BATCH");
+    const int want = e ? atoi(e) : 4;
+    g.bmax = want < 1 ? 1 : (want < g.sa ? want : g.sa);
+  }
   const size_t smem = g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb);
   if (smem > kSmemBudget) {
     set_error("lg_conv_wgrad_tc: shared memory %zu exceeds the budget (Cin=%d Cout=%d)", smem, Cin, Cout);
