@@ -29,6 +29,9 @@ METRIC = "lidog_train_scans_per_s"
 UNIT = "scans/s"
 
 
+CONFIG_OF_SHAPE = {"kitti": "configs[1]", "nuscenes": "configs[2]", "mix3d": "configs[4]"}
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -36,7 +39,9 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=8, help="scans per GPU (BASELINE configs[1]: 8)")
-    p.add_argument("--shape", default="kitti", choices=["kitti", "nuscenes"])
+    p.add_argument("--shape", default="kitti", choices=["kitti", "nuscenes", "mix3d"],
+                   help="kitti = BASELINE configs[1] (the headline); nuscenes = configs[2] (use --batch 16); "
+                        "mix3d = configs[4] (two merged scans per sample)")
     p.add_argument("--classes", type=int, default=7)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-baseline-seconds", type=float, default=30.0)
@@ -167,7 +172,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LiDOG MinkUNet34BEV training step, synthetic {args.shape}-shaped scans, "
-                                   f"{args.classes} classes (BASELINE configs[1])", "sample": sample},
+                                   f"{args.classes} classes (BASELINE {CONFIG_OF_SHAPE[args.shape]})", "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -342,11 +347,12 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"LiDOG MinkUNet34BEV training step (voxelise + maps + sparse conv fwd/bwd + BEV "
                                        f"projection + cuDNN 2D head + losses + Adam), synthetic {args.shape}-shaped "
-                                       f"scans, batch {args.batch}/GPU, {args.classes} classes (BASELINE configs[1])",
+                                       f"scans, batch {args.batch}/GPU, {args.classes} classes "
+                                       f"(BASELINE {CONFIG_OF_SHAPE[args.shape]})",
                            "points_per_step_per_gpu": n_points, "global_batch": world * args.batch,
                            "parallelism": f"dp{world}" + (" (DDP + SyncBN over NCCL)" if world > 1 else ""),
                            "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",
-                           "conv_operands": meconv.CONFIG["tc"], "gather": {0: "cp.async v1", 1: "tma_gather4 v1", 2: "cp.async+mbarrier super-tile v3, mask-sorted plans"}[meconv.CONFIG["gather"]],
+                           "conv_operands": meconv.CONFIG["tc"], "gather": {0: "cp.async v1", 1: "tma_gather4 v1", 2: "cp.async+mbarrier super-tile v4 (batched MMA-warp waits), mask-sorted plans"}[meconv.CONFIG["gather"]],
                            "fused_bn": bool(menorm.CONFIG["fused"]),
                            "bev_layout": "channels_last" if lbev.CONFIG["channels_last"] else "nchw"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

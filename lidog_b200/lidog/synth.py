@@ -18,6 +18,8 @@ SHAPES = {
     # beams, azimuth steps, elevation range (deg), BEV bound (m), BEV label image size
     "kitti": dict(beams=64, azimuth=2083, el=(-24.8, 2.0), bound=50.0, bev_img=167),
     "nuscenes": dict(beams=32, azimuth=1090, el=(-30.0, 10.0), bound=30.0, bev_img=100),
+    # BASELINE configs[4]: two kitti-shaped scans merged and re-quantised the way utils/datasets/mix3D.py:43-87 does
+    "mix3d": dict(beams=64, azimuth=2083, el=(-24.8, 2.0), bound=50.0, bev_img=167, mix_of="kitti"),
 }
 
 
@@ -29,9 +31,35 @@ def _ray_dirs(beams, azimuth, el_range):
     return d.reshape(-1, 3)
 
 
+def _quantize_first(points: np.ndarray, labels: np.ndarray, voxel_size: float):
+    """The dataset-side sparse_quantize of ONE source scan, reduced to what the merge needs: integer voxel
+    coordinates (first occurrence order) and the first point's label (semantickitti_bev.py:232-244)."""
+    q = np.floor(points / np.float32(voxel_size)).astype(np.int32)
+    _, first = np.unique(q, axis=0, return_index=True)
+    first = np.sort(first)
+    return q[first], labels[first]
+
+
+def make_mix3d_scan(seed: int, num_classes: int = 7, voxel_size: float = 0.05, source: str = "kitti"):
+    """Mix3D-shaped sample (utils/datasets/mix3D.py:43-87): two source scans, each already voxelised by its
+    dataset, are turned back into metric float32 coordinates (`coordinates * voxel_size`, `:45-46`), concatenated
+    (`:60`) and handed to sparse_quantize again (`:67-72`).  float32(c * 0.05) / 0.05 floors to c - 1 for ~6 %
+    of the integers (SURVEY.md section 8a note), so the merged voxel set is NOT the union of the two source sets;
+    returning the metric points keeps that arithmetic inside the (GPU) voxelisation under test."""
+    parts, labs = [], []
+    for j in range(2):
+        pts, lab = make_scan(seed + 5003 * j, source, num_classes)
+        q, l = _quantize_first(pts, lab, voxel_size)
+        parts.append((q.astype(np.float32) * np.float32(voxel_size)).astype(np.float32))
+        labs.append(l)
+    return np.concatenate(parts, 0), np.concatenate(labs, 0).astype(np.int32)
+
+
 def make_scan(seed: int, shape: str = "kitti", num_classes: int = 7, max_range: float = 50.0):
     """-> (points float32 [N,3], labels int32 [N]) after LiDOG's crop/filters."""
     cfg = SHAPES[shape]
+    if "mix_of" in cfg:
+        return make_mix3d_scan(seed, num_classes, source=cfg["mix_of"])
     rng = np.random.default_rng(seed)
     d = _ray_dirs(cfg["beams"], cfg["azimuth"], cfg["el"])
     n = d.shape[0]

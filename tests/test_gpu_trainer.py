@@ -1,0 +1,88 @@
+"""GPU parity of one whole LiDOG training step (PLTTrainer2D.training_step, trainer_lighting_2d.py:141-293)
+against the same step on the CPU oracle: batched voxelisation, BEV label image, MinkUNet34BEV, both DICE
+losses, backward, Adam.  Inputs: a batch of two small scans -- one nuScenes-shaped crop and one Mix3D-shaped
+merge (two crops re-quantised through float32 metres, utils/datasets/mix3D.py:43-87).
+
+Tolerances: losses within 2e-3 (fp32 SIMT convolutions) / 3e-2 (fp16 tensor-core operands, 63 layers deep);
+parameters after the Adam step are compared through the update direction of the well-conditioned ones.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _crop(pts, lab, r):
+    keep = (np.abs(pts[:, 0]) < r) & (np.abs(pts[:, 1]) < r)
+    return pts[keep], lab[keep]
+
+
+def _batch():
+    from lidog_b200.lidog import synth
+    a, la = _crop(*synth.make_scan(11, "nuscenes"), 9.0)
+    # Mix3D-shaped: two crops, each snapped to its voxel grid, turned back into float32 metres, concatenated
+    parts, labs = [], []
+    for seed in (12, 13):
+        p, l = _crop(*synth.make_scan(seed, "nuscenes"), 7.0)
+        q, l1 = synth._quantize_first(p, l, 0.05)
+        parts.append((q.astype(np.float32) * np.float32(0.05)).astype(np.float32))
+        labs.append(l1)
+    return [a, np.concatenate(parts)], [la, np.concatenate(labs).astype(np.int32)]
+
+
+@pytest.mark.parametrize("mode,tol", [("off", 2e-3), ("fp16", 3e-2)])
+def test_training_step_matches_oracle(cuda, mode, tol):
+    import MinkowskiEngine as ME
+    from lidog_b200.me import conv as meconv
+    from lidog_b200.lidog import model as M, step
+    from oracle import me_cpu
+    from oracle.me_cpu.bevfn import sparse2super as o_s2s
+
+    pts, lab = _batch()
+    torch.manual_seed(0)
+    ref_net = M.MinkUNet34BEV(1, 7, ME=me_cpu, bev_fn=o_s2s, mapping_bound_2d=30.0)
+    state = {k: v.clone() for k, v in ref_net.state_dict().items()}
+    ref = step.LidogTrainer(ref_net, num_classes=7, shape="nuscenes", ME=me_cpu)
+    P, L = [torch.from_numpy(p) for p in pts], [torch.from_numpy(l) for l in lab]
+    # voxelisation + label products of the oracle trainer, then its loss terms
+    c_o, f_o, sem_o, bev_o, cm_o = ref.voxelize(P, L)
+    tot_o, l3_o, l2_o = ref.forward_loss(c_o, f_o, sem_o, bev_o, len(P), cm_o)
+    ref.optimizer.zero_grad(set_to_none=True)
+    tot_o.backward()
+    ref.optimizer.step()
+
+    old = dict(meconv.CONFIG)
+    meconv.CONFIG["tc"] = mode
+    try:
+        net = M.MinkUNet34BEV(1, 7, mapping_bound_2d=30.0)
+        net.load_state_dict(state)
+        net = net.to(cuda)
+        tr = step.LidogTrainer(net, num_classes=7, shape="nuscenes")
+        Pd, Ld = [p.to(cuda) for p in P], [l.to(cuda) for l in L]
+        c, f, sem, bev, cm = tr.voxelize(Pd, Ld)
+        # integer products of the data path: bit exact
+        assert torch.equal(c.cpu(), c_o.to(torch.int32)), "batched voxel coordinates differ"
+        assert torch.equal(sem.cpu(), sem_o), "per-voxel 3D labels differ"
+        assert torch.equal(bev.cpu(), bev_o), "BEV label images differ"
+        tot, l3, l2 = tr.forward_loss(c, f, sem, bev, len(Pd), cm)
+        tr.optimizer.zero_grad(set_to_none=True)
+        tot.backward()
+        tr.optimizer.step()
+        torch.cuda.synchronize()
+    finally:
+        meconv.CONFIG.update(old)
+
+    for name, a, b in (("3d", l3, l3_o), ("bev", l2, l2_o), ("total", tot, tot_o)):
+        assert abs(float(a) - float(b)) <= tol * max(1.0, abs(float(b))), (name, float(a), float(b))
+    # Adam's first step moves every weight by lr * sign-like(g): compare the update of parameters whose gradient
+    # is far from zero (the sign of a ~0 gradient is noise in both implementations)
+    new_o = dict(ref_net.named_parameters())
+    agree, total = 0, 0
+    for name, p in net.named_parameters():
+        d = (p.detach().cpu() - state[name]).flatten()
+        d_o = (new_o[name].detach() - state[name]).flatten()
+        big = d_o.abs() > 0.5e-3  # |update| ~ lr = 1e-3 where |g| >> eps
+        total += int(big.sum())
+        agree += int((torch.sign(d[big]) == torch.sign(d_o[big])).sum())
+    assert total > 0 and agree / total > 0.97, (agree, total)
