@@ -54,13 +54,15 @@ __device__ __forceinline__ unsigned long long pack_key(int b, int x, int y, int 
          ((unsigned long long)(unsigned)(y + kCoordBias) << 16) | (unsigned long long)(unsigned)(z + kCoordBias);
 }
 
+// 32-bit multiplicative mix of the packed key (3 IMUL + 4 shifts/xors).  The 64-bit murmur finaliser used at first
+// cost ~40 instructions per probe (two 64-bit multiplies), a third of k_neighbors' issue-bound time; table contents
+// and every result are independent of the hash function (first occurrence wins by atomicMin on the row).
 __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return k;
+  unsigned int h = (unsigned int)k * 0x9E3779B1u ^ (unsigned int)(k >> 32) * 0x85EBCA77u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return (unsigned long long)h;
 }
 
 // Returns the row id stored for `key`, or -1.

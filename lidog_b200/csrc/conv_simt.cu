@@ -315,15 +315,24 @@ __global__ void __launch_bounds__(256, 1)
 // read / write the wide matrix once, coalesced (8 lanes per 128 bytes of a row).
 constexpr int HD_N = 8;      // padded narrow width
 constexpr int HD_CMAX = 256; // widest wide matrix
+// Shared-memory slot of channel c of the narrow weight matrix.  The 8 lanes of a row read channels 4*(l8 + 8t) + i
+// at the same time; stored at [channel] they all fell into the same 4 banks (a 128-bit load is served a quarter warp
+// at a time: 8-way conflict, 32 wavefronts per instruction -- the first version ran at 0.5 TB/s because of it).
+// Slot ((t * 4 + i) * 8 + l8) makes those 8 lanes read 8 consecutive 16-byte words: conflict free.
+__device__ __forceinline__ int hd_slot(int c) {
+  const int c4 = c >> 2, i = c & 3;
+  return (((c4 >> 3) * 4 + i) << 3) + (c4 & 7);
+}
 
 // Y[s][0..n) = A[nbr[s]][:] @ W (C x n, row-major, n <= 8) + bias.  8 lanes per row, 4 rows per warp.
 __global__ void __launch_bounds__(256)
     k_head_fwd(lgConvPlan plan, const float* __restrict__ A, int C, const float* __restrict__ W, int n,
                const float* __restrict__ bias, float* __restrict__ Y) {
-  __shared__ __align__(16) float Ws[HD_CMAX][HD_N];
+  __shared__ __align__(16) float Wlo[HD_CMAX][4], Whi[HD_CMAX][4];
   for (int e = threadIdx.x; e < C * HD_N; e += 256) {
     const int c = e / HD_N, j = e % HD_N;
-    Ws[c][j] = j < n ? W[c * n + j] : 0.f;
+    const float w = j < n ? W[c * n + j] : 0.f;
+    if (j < 4) Wlo[hd_slot(c)][j] = w; else Whi[hd_slot(c)][j - 4] = w;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, l8 = lane & 7;
@@ -339,17 +348,25 @@ __global__ void __launch_bounds__(256)
       for (int j = 0; j < HD_N; ++j) acc[j] = 0.f;
       if (row >= 0) {
         const float4* a4 = reinterpret_cast<const float4*>(A + (int64_t)row * C);
-        for (int c4 = l8; c4 < C / 4; c4 += 8) {
-          const float4 a = __ldg(a4 + c4);
-          const float av[4] = {a.x, a.y, a.z, a.w};
+        const int nt = C >> 5;  // float4 per lane
+        float4 a[HD_CMAX / 32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][0]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][4]);
-            acc[0] = fmaf(av[i], w0.x, acc[0]); acc[1] = fmaf(av[i], w0.y, acc[1]);
-            acc[2] = fmaf(av[i], w0.z, acc[2]); acc[3] = fmaf(av[i], w0.w, acc[3]);
-            acc[4] = fmaf(av[i], w1.x, acc[4]); acc[5] = fmaf(av[i], w1.y, acc[5]);
-            acc[6] = fmaf(av[i], w1.z, acc[6]); acc[7] = fmaf(av[i], w1.w, acc[7]);
+        for (int t = 0; t < HD_CMAX / 32; ++t)  // all loads of the row before the first use
+          if (t < nt) a[t] = __ldg(a4 + l8 + 8 * t);
+#pragma unroll
+        for (int t = 0; t < HD_CMAX / 32; ++t) {
+          if (t < nt) {
+            const float av[4] = {a[t].x, a[t].y, a[t].z, a[t].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int slot = ((t * 4 + i) << 3) + l8;  // = hd_slot(4 * (l8 + 8 t) + i)
+              const float4 w0 = *reinterpret_cast<const float4*>(&Wlo[slot][0]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&Whi[slot][0]);
+              acc[0] = fmaf(av[i], w0.x, acc[0]); acc[1] = fmaf(av[i], w0.y, acc[1]);
+              acc[2] = fmaf(av[i], w0.z, acc[2]); acc[3] = fmaf(av[i], w0.w, acc[3]);
+              acc[4] = fmaf(av[i], w1.x, acc[4]); acc[5] = fmaf(av[i], w1.y, acc[5]);
+              acc[6] = fmaf(av[i], w1.z, acc[6]); acc[7] = fmaf(av[i], w1.w, acc[7]);
+            }
           }
         }
       }
@@ -370,10 +387,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_head_dgrad(lgConvPlan plan, const float* __restrict__ dY, int n, const float* __restrict__ W, int C,
                  float* __restrict__ dX) {
-  __shared__ __align__(16) float Ws[HD_CMAX][HD_N];
+  __shared__ __align__(16) float Wlo[HD_CMAX][4], Whi[HD_CMAX][4];
   for (int e = threadIdx.x; e < C * HD_N; e += 256) {
     const int c = e / HD_N, j = e % HD_N;
-    Ws[c][j] = j < n ? W[c * n + j] : 0.f;
+    const float w = j < n ? W[c * n + j] : 0.f;
+    if (j < 4) Wlo[hd_slot(c)][j] = w; else Whi[hd_slot(c)][j - 4] = w;
   }
   __syncthreads();
   const int l8 = threadIdx.x & 7;
@@ -387,8 +405,8 @@ __global__ void __launch_bounds__(256)
       float o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[4 * c4 + i][4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&Wlo[hd_slot(4 * c4 + i)][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Whi[hd_slot(4 * c4 + i)][0]);
         float a = g[0] * w0.x;
         a = fmaf(g[1], w0.y, a); a = fmaf(g[2], w0.z, a); a = fmaf(g[3], w0.w, a);
         a = fmaf(g[4], w1.x, a); a = fmaf(g[5], w1.y, a); a = fmaf(g[6], w1.z, a); a = fmaf(g[7], w1.w, a);

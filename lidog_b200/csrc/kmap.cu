@@ -27,62 +27,26 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
   const int base = (ksize & 1) ? -(ksize / 2) : 0;
   uint32_t wmask[kMaxMaskWords] = {0, 0, 0, 0};
   uint32_t rmask = 0;  // this row's offsets (sorted plans only, K <= 32)
+  // (Issuing the first probes of a whole kernel x-row together was tried: 64 instead of 32 registers halved the
+  // occupancy and the 125-offset map went 567 -> 736 us.  ncu: 360 M warp instructions for 81 M probes -- the
+  // kernel is issue-bound, so the instruction count per probe is what matters; see hash_key in common.cuh.)
   int k = 0;
-  // One x-row of the kernel (<= 5 offsets) per round: the first probes of the row are issued together and
-  // resolved afterwards.  The one-offset-at-a-time loop was a chain of K dependent L2 round trips per thread
-  // (ncu: 8 % of peak DRAM, 45 % L2 throughput, 567 us for the 125-offset stem map).
-  constexpr int kRow = 5;
   for (int iz = 0; iz < ksize; ++iz)
-    for (int iy = 0; iy < ksize; ++iy) {
-      unsigned long long key[kRow], slot[kRow];
-      ulonglong2 raw[kRow];
-      bool live[kRow];
-      const int y = c.z + (base + iy) * scale, z = c.w + (base + iz) * scale;
-#pragma unroll
-      for (int ix = 0; ix < kRow; ++ix) {
-        live[ix] = false;
-        if (ix < ksize) {
-          const int x = c.y + (base + ix) * scale;
-          live[ix] = valid && coord_in_range(c.x, x, y, z);
-          if (live[ix]) {
-            key[ix] = pack_key(c.x, x, y, z);
-            slot[ix] = hash_key(key[ix]) & mask;
-            raw[ix] = __ldg(reinterpret_cast<const ulonglong2*>(table + slot[ix]));
-          }
+    for (int iy = 0; iy < ksize; ++iy)
+      for (int ix = 0; ix < ksize; ++ix, ++k) {
+        int r = -1;
+        if (valid) {
+          int x = c.y + (base + ix) * scale, y = c.z + (base + iy) * scale, z = c.w + (base + iz) * scale;
+          if (coord_in_range(c.x, x, y, z)) r = hash_lookup(table, mask, pack_key(c.x, x, y, z));
+        }
+        nbr[(int64_t)k * n_slots + o] = r;
+        const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
+        if (bal) wmask[k >> 5] |= 1u << (k & 31);
+        if (row_mask) {
+          rmask |= (r >= 0 ? 1u : 0u) << (k & 31);
+          if (bal && (threadIdx.x & 31) == 0) atomicAdd(&k_count[k], (unsigned)__popc(bal));
         }
       }
-#pragma unroll
-      for (int ix = 0; ix < kRow; ++ix) {
-        if (ix < ksize) {
-          int r = -1;
-          if (live[ix]) {
-            ulonglong2 v = raw[ix];
-            unsigned long long s = slot[ix];
-            for (;;) {  // linear probing; the first slot decides for most keys (load factor <= 0.5)
-              if (v.x == key[ix]) {
-                r = (int)(unsigned)(v.y & 0xFFFFFFFFull);
-                break;
-              }
-              if (v.x == kEmptyKey) break;
-              s = (s + 1) & mask;
-              v = __ldg(reinterpret_cast<const ulonglong2*>(table + s));
-            }
-          }
-          nbr[(int64_t)k * n_slots + o] = r;
-          const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
-          if (bal) {
-#pragma unroll
-            for (int w = 0; w < kMaxMaskWords; ++w)
-              if ((k >> 5) == w) wmask[w] |= 1u << (k & 31);
-          }
-          if (row_mask) {
-            rmask |= (r >= 0 ? 1u : 0u) << (k & 31);
-            if (bal && (threadIdx.x & 31) == 0) atomicAdd(&k_count[k], (unsigned)__popc(bal));
-          }
-          ++k;
-        }
-      }
-    }
   if (row_mask) row_mask[o] = rmask;
   if ((threadIdx.x & 31) == 0) {
     for (int w = 0; w < mask_words; ++w)

@@ -3,8 +3,8 @@ against the same step on the CPU oracle: batched voxelisation, BEV label image, 
 losses, backward, Adam.  Inputs: a batch of two small scans -- one nuScenes-shaped crop and one Mix3D-shaped
 merge (two crops re-quantised through float32 metres, utils/datasets/mix3D.py:43-87).
 
-Tolerances: losses within 2e-3 (fp32 SIMT convolutions) / 3e-2 (fp16 tensor-core operands, 63 layers deep);
-parameters after the Adam step are compared through the update direction of the well-conditioned ones.
+Tolerances: integer products of the data path bit exact; losses within 2e-3 (fp32 SIMT convolutions) / 3e-2 (fp16
+tensor-core operands, 63 layers deep); parameter gradients within 20x that, layer by layer.
 """
 import numpy as np
 import pytest
@@ -75,14 +75,23 @@ def test_training_step_matches_oracle(cuda, mode, tol):
 
     for name, a, b in (("3d", l3, l3_o), ("bev", l2, l2_o), ("total", tot, tot_o)):
         assert abs(float(a) - float(b)) <= tol * max(1.0, abs(float(b))), (name, float(a), float(b))
-    # Adam's first step moves every weight by lr * sign-like(g): compare the update of parameters whose gradient
-    # is far from zero (the sign of a ~0 gradient is noise in both implementations)
-    new_o = dict(ref_net.named_parameters())
-    agree, total = 0, 0
+    # gradients, layer by layer (they pass through 62 BN layers: looser than the per-layer bar, as in test_gpu_model)
+    def rel(a, b):
+        return float((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm().clamp_min(1e-30))
+
+    ref_params = dict(ref_net.named_parameters())
+    worst, worst_name = 0.0, None
     for name, p in net.named_parameters():
-        d = (p.detach().cpu() - state[name]).flatten()
-        d_o = (new_o[name].detach() - state[name]).flatten()
-        big = d_o.abs() > 0.5e-3  # |update| ~ lr = 1e-3 where |g| >> eps
-        total += int(big.sum())
-        agree += int((torch.sign(d[big]) == torch.sign(d_o[big])).sum())
-    assert total > 0 and agree / total > 0.97, (agree, total)
+        g, go = p.grad, ref_params[name].grad
+        assert g is not None and go is not None and torch.isfinite(g).all(), name
+        if float(go.norm()) > 1e-10:
+            e = rel(g, go)
+            if e > worst:
+                worst, worst_name = e, name
+    assert worst <= 20 * tol, (worst_name, worst)
+    # Adam moved the weights (|update| ~ lr on the first step) and nothing blew up
+    moved = 0.0
+    for name, p in net.named_parameters():
+        assert torch.isfinite(p).all(), name
+        moved = max(moved, float((p.detach().cpu() - state[name]).abs().max()))
+    assert 0.5e-3 < moved < 2e-3, moved
