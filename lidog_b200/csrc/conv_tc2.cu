@@ -193,7 +193,8 @@ struct Gemm2Args {
   const float* out_scale;
   const float* bias;
   int Ck, N, n_blk, flip, umma_fmt;
-  int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs
+  int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs, 16 = no proxy fence,
+            // 32 = no result stores, 64 = no row-id copies (8 = per-role cycle counters of CTA 0)
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
   int pf;                           // id warp prefetches the operand rows of upcoming units into L2
   int bmax;                         // units the MMA warp waits for together (one proxy fence per batch), <= sa
@@ -310,10 +311,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             const int t = __ffs(mm) - 1;
             mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
-              bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
-                            g.plan.nbr + (int64_t)k * g.plan.k_stride + (tile0 + t) * LG_TILE_ROWS, kIdxSlotBytes,
-                            &fullI[slot]);
+              if (g.dbg & 64) {  // experiment: no id copies (the producers gather whatever the ring holds)
+                mbar_arrive(&fullI[slot]);
+              } else {
+                mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
+                bulk_copy_g2s(smI + (size_t)slot * kIdxSlotBytes,
+                              g.plan.nbr + (int64_t)k * g.plan.k_stride + (tile0 + t) * LG_TILE_ROWS, kIdxSlotBytes,
+                              &fullI[slot]);
+              }
             }
             __syncwarp();
             if (++slot == ni) {
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
-                if (srow[j] >= 0)
+                if (srow[j] >= 0 && !(g.dbg & 32))  // dbg 32: experiment without the result stores
                   *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
               }
               __syncwarp();

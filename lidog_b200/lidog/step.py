@@ -21,12 +21,18 @@ def bev_label_image(coords4: torch.Tensor, colabels: torch.Tensor, batch_size: i
     """Device version of PC2ImgConverter.getBEVImageNew (semantickitti_bev.py:433-464) for a whole
     batch: int64 [B, img, img], -1 = ignore.  Duplicate pixels: highest row wins (deterministic)."""
     dev = coords4.device
-    pts = coords4[:, 1:].to(torch.float32) * voxel_size
+    # `(quantized_coords * voxel_size).astype(np.float32)` (semantickitti_bev.py:244): an int32 array times a python
+    # float is a DOUBLE product rounded once to float32 -- not float32(c) * float32(0.05) as in sparse2super
+    pts = (coords4[:, 1:].to(torch.float64) * voxel_size).to(torch.float32)
     grid = (bound - (-bound)) / img
     valid = (colabels != -1) & (-bound < pts[:, 0]) & (pts[:, 0] < bound) & (-bound < pts[:, 1]) & \
             (pts[:, 1] < bound) & (-10 < pts[:, 2]) & (pts[:, 2] < 8)
-    px = torch.floor((pts[:, 0] - (-bound)) / grid).long()
-    py = torch.floor(img - (pts[:, 1] - (-bound)) / grid).long() - 1
+    # torch's CUDA kernel for `tensor / python_scalar` multiplies by the reciprocal; the reference divides (numpy
+    # float32, IEEE), and floor() of the two differs on cell boundaries -- divide by a TENSOR to get the true quotient
+    # (found by tests/test_gpu_trainer.py against the CPU evaluation of this same function)
+    grid_t = torch.tensor(grid, dtype=torch.float32, device=dev)
+    px = torch.floor(torch.div(pts[:, 0] - (-bound), grid_t)).long()
+    py = torch.floor(img - torch.div(pts[:, 1] - (-bound), grid_t)).long() - 1
     py = torch.where(py < 0, py + img, py)
     pix = coords4[:, 0].long() * (img * img) + py.clamp(0, img - 1) * img + px.clamp(0, img - 1)
     rows = torch.arange(coords4.shape[0], device=dev)

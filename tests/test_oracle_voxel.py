@@ -97,3 +97,21 @@ def test_synthetic_scan_shapes():
     assert np.abs(q[:, :2]).max() < 1200 and q[:, 2].min() >= -200 and q[:, 2].max() < 160
     pts, _ = synth.make_scan(7, "nuscenes")
     assert 25_000 < len(pts) < 40_000
+
+
+def test_bev_label_image_matches_numpy_restatement():
+    """`bev_label_image` (the batched torch version the trainer runs, CPU here / CUDA in tests/test_gpu_trainer.py)
+    against the numpy restatement of PC2ImgConverter.getBEVImageNew (semantickitti_bev.py:433-464): float32
+    subtract, TRUE float32 division by the grid size, floor, last writer wins."""
+    import torch
+    from lidog_b200.lidog import synth
+    from lidog_b200.lidog.step import bev_label_image
+    for seed, shape in ((3, "nuscenes"), (4, "kitti")):
+        cfg = synth.SHAPES[shape]
+        pts, lab = synth.make_scan(seed, shape)
+        q, _, colab, _, _ = ov.sparse_quantize(pts, np.ones((len(pts), 1), np.float32), lab, -1, True, True, False, 0.05)
+        want = synth.make_bev_labels(q, colab, cfg["bound"], cfg["bev_img"])
+        c4 = torch.from_numpy(np.concatenate([np.zeros((len(q), 1), np.int32), q], 1))
+        got = bev_label_image(c4, torch.from_numpy(colab), 1, cfg["bound"], cfg["bev_img"])
+        assert got.shape == (1, cfg["bev_img"], cfg["bev_img"])
+        assert np.array_equal(got[0].numpy(), want)
