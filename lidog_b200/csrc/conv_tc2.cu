@@ -35,9 +35,19 @@ using namespace ptx;
 
 // LIDOG_DBG & 8: CTA 0 accumulates the cycles each role spends waiting (read back by lg_debug_profile)
 __device__ long long g_prof[16];
-#define PROF_T0() long long _t0 = clock64()
-#define PROF_ADD(slot) do { if (prof) { long long _t1 = clock64(); pacc[slot] += _t1 - _t0; _t0 = _t1; } } while (0)
-#define PROF_FLUSH(lo, hi) do { if (prof) for (int _i = lo; _i <= hi; ++_i) g_prof[_i] += pacc[_i]; } while (0)
+// LIDOG_DBG & 8: event trace of CTA 0, [event][unit] = clock64 for the first kTraceUnits units of the launch:
+// 0 producer got the free stage, 1 producer armed the stage barrier, 2 MMA warp saw the stage full, 3 MMA warp
+// committed the unit, 4 id copy issued (read back by lg_debug_trace)
+constexpr int kTraceUnits = 512;
+__device__ long long g_trace[5][kTraceUnits];
+// The instrumentation exists only in the DBG instantiation of the kernel (LIDOG_DBG != 0 selects it): in the
+// production instantiation every macro below compiles to nothing.  (The event trace showed the one-thread MMA role
+// executing ~500 instructions per (offset, panel) step at ~5 cycles each -- it, not the data movement or the tensor
+// pipe, set the pace -- and a third of those instructions were predicated-off instrumentation and switches.)
+#define TRACE(ev, unit) do { if (DBG && prof && (unit) < kTraceUnits) g_trace[ev][unit] = clock64(); } while (0)
+#define PROF_T0() long long _t0 = DBG ? clock64() : 0
+#define PROF_ADD(slot) do { if (DBG && prof) { long long _t1 = clock64(); pacc[slot] += _t1 - _t0; _t0 = _t1; } } while (0)
+#define PROF_FLUSH(lo, hi) do { if (DBG && prof) for (int _i = lo; _i <= hi; ++_i) g_prof[_i] += pacc[_i]; } while (0)
 
 constexpr int kRowB = 64;            // bytes per smem operand row (32 x 16-bit)
 constexpr int kSub = 128 * kRowB;    // one [128 rows x 32 channels] sub-tile = 8 KB
@@ -194,7 +204,8 @@ struct Gemm2Args {
   const float* bias;
   int Ck, N, n_blk, flip, umma_fmt;
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs, 16 = no proxy fence,
-            // 32 = no result stores, 64 = no row-id copies (8 = per-role cycle counters of CTA 0)
+            // 32 = no result stores, 64 = no row-id copies, 128 = stage release by plain arrive (only with 4);
+            // 8 = per-role cycle counters of CTA 0
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
   int pf;                           // id warp prefetches the operand rows of upcoming units into L2
   int bmax;                         // units the MMA warp waits for together (one proxy fence per batch), <= sa
@@ -205,11 +216,13 @@ struct Gemm2Args {
   int* sched;  // [0..3] next super-tile per blockIdx.y, [4] finished CTAs (self-resetting)
 };
 
+// DBG: instrumentation + experiment switches compiled in.  PC: 32-channel chunks per operand stage (= g.pc).
+template <bool DBG, int PC>
 __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stageA = g.pc * kSub, stageB = g.pc * g.n_blk * kRowB;
+  const int stageA = PC * kSub, stageB = PC * g.n_blk * kRowB;
   uint8_t* smA = smem;
   uint8_t* smB = smem + (size_t)g.sa * stageA;
   uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
@@ -230,9 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   SchedCursor sc{0, 0};
   const int n0 = blockIdx.y * g.n_blk;
   const int K = g.plan.kernel_volume;
-  const bool prof = (g.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
-  long long pacc[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const long long cta_t0 = clock64();
+  const int dbg = DBG ? g.dbg : 0;  // experiment switches fold away in the production instantiation
+  const bool prof = DBG && (dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long cta_t0 = DBG ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.sa; ++s) {
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     // cp.async.bulk.prefetch.L2 per unit made every layer 1.2-6x SLOWER (0.229 -> 0.834 ms on the block8 shape);
     // the bulk-prefetch path serialises far below the rate the LDGSTS gathers sustain.  Kept as the record.
     constexpr int kPfLag = 8;
-    int pslot = 0, pf_count = 0;
+    int pslot = 0, pf_count = 0, iunit = 0;
     uint32_t pphase = 0, pf_hist = 0;
     const uint32_t row_bytes = (uint32_t)g.Ck * 2u;
     for (;;) {
@@ -309,9 +323,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
         for (int p = 0; p < g.n_panels; ++p) {
           for (uint32_t mm = m; mm; mm &= mm - 1) {
             const int t = __ffs(mm) - 1;
-            mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
+            if (!(dbg & 512)) mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 7);
+            TRACE(4, iunit);
+            ++iunit;
             if (elect_one()) {
-              if (g.dbg & 64) {  // experiment: no id copies (the producers gather whatever the ring holds)
+              if (dbg & 64) {  // experiment: no id copies (the producers gather whatever the ring holds)
                 mbar_arrive(&fullI[slot]);
               } else {
                 mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   } else if (warp >= kProdWarp0) {
     // ===================================================================== A producers (cp.async gather)
     const int pw = warp - kProdWarp0;
-    int stage = 0, turn = 0, slot = 0;
+    int stage = 0, turn = 0, slot = 0, punit = 0;
     uint32_t phase = 0, iphase = 0;
     SchedItem item;
     for (;;) {
@@ -367,20 +383,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             if (turn == pw) {
               PROF_T0();
               int rows[16];
-              mbar_wait(&fullI[slot], iphase, g.err, 8);
-              ids_from_ring(rows, smem_u32(smI) + slot * kIdxSlotBytes, lane);
-              __syncwarp();
-              if (lane == 0) {
-                mbar_arrive(&emptyI[slot]);
-                mbar_wait(&emptyA[stage], phase ^ 1, g.err, 1);
+              if (!(dbg & 512)) {  // dbg 512: experiment without the id ring on the producer side
+                mbar_wait(&fullI[slot], iphase, g.err, 8);
+                ids_from_ring(rows, smem_u32(smI) + slot * kIdxSlotBytes, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyI[slot]);
               }
+              if (pw == 0) PROF_ADD(15);
+              if (lane == 0) mbar_wait(&emptyA[stage], phase ^ 1, g.err, 1);
               __syncwarp();
+              TRACE(0, punit);
               if (pw == 0) PROF_ADD(0);
-              if (!(g.dbg & 2))
-                gather_stage(smA + (size_t)stage * stageA, g.A, g.Ck, p * g.pc * 32, g.pc, rows, lane);
-              cp_async_arrive_noinc(&fullA[stage]);
+              if (!(dbg & 2))
+                gather_rows<PC>(smA + (size_t)stage * stageA, reinterpret_cast<const uint8_t*>(g.A + p * PC * 32), (uint32_t)g.Ck * 2u, rows, lane);
+              if (dbg & 256)  // experiment (with dbg 2 only): plain arrive instead of the cp.async-tracked one
+                mbar_arrive(&fullA[stage]);
+              else
+                cp_async_arrive_noinc(&fullA[stage]);
+              TRACE(1, punit);
               if (pw == 0) PROF_ADD(1);
             }
+            ++punit;
             turn = (turn + 1 == g.np) ? 0 : turn + 1;
             if (++stage == g.sa) {
               stage = 0;
@@ -414,13 +437,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
           mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 2);
           PROF_ADD(2);
           if (elect_one()) {
-            if (g.dbg & 1) {
+            if (dbg & 1) {
               mbar_arrive(&fullB[bs]);
             } else {
               mbar_arrive_expect_tx(&fullB[bs], (uint32_t)stageB);
               uint8_t* dst = smB + (size_t)bs * stageB;
-              for (int c = 0; c < g.pc; ++c)
-                tma_load_2d(dst + c * g.n_blk * kRowB, &tmB, (p * g.pc + c) * 32, wk * g.N + n0, &fullB[bs]);
+#pragma unroll
+              for (int c = 0; c < PC; ++c)
+                tma_load_2d(dst + c * g.n_blk * kRowB, &tmB, (p * PC + c) * 32, wk * g.N + n0, &fullB[bs]);
             }
           }
           __syncwarp();
@@ -443,8 +467,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
     const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
     const uint32_t b_sub16 = (uint32_t)(g.n_blk * kRowB) >> 4;
-    const int pc = g.pc;
-    int stage = 0, bs = 0;
+    // everything the loop needs lives in registers: no parameter loads, no 64-bit index arithmetic in the hot path
+    const int sa = g.sa, sb = g.sb, T = g.T, n_panels = g.n_panels, n_blk = g.n_blk, two_sets = g.sets == 2;
+    int stage = 0, bs = 0, munit = 0;
     uint32_t phase = 0, bphase = 0, it = 0;
     SchedItem item;
     for (;;) {
@@ -452,102 +477,94 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       sched_next(item, sc, fullS, emptyS, sched_ring, lane, g.err);
       const int64_t st = item.st;
       if (st < 0) break;
-      const int64_t tile0 = st * g.T;
-      const int nt = (int)min((int64_t)g.T, g.n_tiles - tile0);
+      const int64_t tile0 = st * T;
+      const int nt = (int)min((int64_t)T, g.n_tiles - tile0);
       if (!item.any) continue;
-      const int set = (g.sets == 2) ? (int)(it & 1) : 0;
-      const uint32_t eparity = (((g.sets == 2) ? (it >> 1) : it) & 1) ^ 1;
-      const int a0 = set * g.T;  // first accumulator of this set
+      const int set = two_sets ? (int)(it & 1) : 0;
+      const uint32_t eparity = ((two_sets ? (it >> 1) : it) & 1) ^ 1;
+      const uint32_t d_base = tmem_base + (uint32_t)(set * T) * (uint32_t)n_blk;  // first accumulator of this set
       ++it;
+      // all T accumulators of the set are taken up front (the epilogue hands them back tile by tile; the last one
+      // arrives a few hundred cycles after the first) -- the inner loop then has no hand-off test per unit
+      for (int t = 0; t < T; ++t) mbar_wait(&acc_empty[set * T + t], eparity, g.err, 3);
       uint32_t started = 0;
       TileMasks& tm = item.tm;
       PROF_ADD(11);
       LG_FOR_EACH_OFFSET(tm, g.plan, tile0, nt, k, m) {
-        for (int p = 0; p < g.n_panels; ++p) {
+        for (int p = 0; p < n_panels; ++p) {
           PROF_ADD(7);
           mbar_wait(&fullB[bs], bphase, g.err, 4);
           PROF_ADD(4);
-          const uint64_t db0 = desc_hi | (uint64_t)(b_base + bs * b_stage16);
-          // The units of this (offset, panel) are taken in batches of <= bmax (<= ring depth): wait for all their
-          // stages, ONE proxy fence, then issue them back to back -- the fence and the barrier round trips are
-          // paid per batch instead of per unit.
-          uint32_t mm = m;
-          while (mm) {
-            uint32_t batch = 0;
-            {
-              uint32_t x = mm;
-              for (int i = 0; i < g.bmax && x; ++i) {
-                batch |= x & (0u - x);
-                x &= x - 1;
-              }
-            }
-            mm &= ~batch;
-            {
-              int s = stage;
-              uint32_t ph = phase;
-              for (uint32_t bb = batch; bb; bb &= bb - 1) {
-                const int t = __ffs(bb) - 1;
-                if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
-                mbar_wait(&fullA[s], ph, g.err, 5);
-                if (++s == g.sa) {
-                  s = 0;
-                  ph ^= 1;
-                }
-              }
-            }
-            PROF_ADD(5);
-            if (!(g.dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
-            tc_fence_after();
-            PROF_ADD(10);
-            if (elect_one()) {
-              int s = stage;
-              for (uint32_t bb = batch; bb; bb &= bb - 1) {
-                const int t = __ffs(bb) - 1;
-                const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
-                const uint32_t d_tmem = tmem_base + (a0 + t) * g.n_blk;
-                const uint32_t acc0 = (started >> t) & 1u;
-                if (!(g.dbg & 4)) {
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) {
-                    if (c < pc) {
-                      umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, c == 0 ? acc0 : 1u);
-                      umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
-                    }
-                  }
-                }
-                umma_commit(&emptyA[s]);
-                if (++s == g.sa) s = 0;
-              }
-            }
-            __syncwarp();
-            PROF_ADD(6);
-            started |= batch;
-            for (int i = __popc(batch); i > 0; --i) {
-              pacc[13] += 1;  // units
-              if (++stage == g.sa) {
-                stage = 0;
-                phase ^= 1;
+          const uint32_t db_lo = b_base + bs * b_stage16;
+          // The units of this (offset, panel) -- at most T <= ring depth (host-checked) -- are handled together:
+          // wait for their stages, ONE proxy fence, issue their MMAs back to back, release the stages.
+          {
+            int s = stage;
+            uint32_t ph = phase;
+            for (uint32_t bb = m; bb; bb &= bb - 1) {
+              mbar_wait(&fullA[s], ph, g.err, 5);
+              TRACE(2, munit + __popc(m & ~bb));
+              if (++s == sa) {
+                s = 0;
+                ph ^= 1;
               }
             }
           }
-          if (elect_one()) umma_commit(&emptyB[bs]);
+          PROF_ADD(5);
+          if (!(dbg & 16)) fence_proxy_async();  // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
+          tc_fence_after();
+          PROF_ADD(10);
+          if (elect_one()) {
+            int s = stage;
+            for (uint32_t bb = m; bb; bb &= bb - 1) {
+              const int t = __ffs(bb) - 1;
+              const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
+              const uint64_t db0 = desc_hi | (uint64_t)db_lo;
+              const uint32_t d_tmem = d_base + (uint32_t)t * (uint32_t)n_blk;
+              const uint32_t acc0 = (started >> t) & 1u;
+              if (!(dbg & 4)) {
+#pragma unroll
+                for (int c = 0; c < PC; ++c) {
+                  umma_f16(d_tmem, da0 + c * (kSub >> 4), db0 + c * b_sub16, idesc, c == 0 ? acc0 : 1u);
+                  umma_f16(d_tmem, da0 + c * (kSub >> 4) + 2, db0 + c * b_sub16 + 2, idesc, 1u);
+                }
+              }
+              if (DBG && (dbg & 128))  // experiment (with dbg 4 only): plain arrive instead of tcgen05.commit
+                mbar_arrive(&emptyA[s]);
+              else
+                umma_commit(&emptyA[s]);
+              if (++s == sa) s = 0;
+            }
+            if (DBG && (dbg & 128))
+              mbar_arrive(&emptyB[bs]);
+            else
+              umma_commit(&emptyB[bs]);
+          }
           __syncwarp();
-          if (++bs == g.sb) {
+          if (DBG) {
+            for (int i = 0; i < __popc(m); ++i) TRACE(3, munit + i);
+            munit += __popc(m);
+            pacc[13] += __popc(m);  // units
+          }
+          PROF_ADD(6);
+          started |= m;
+          stage += __popc(m);
+          if (stage >= sa) {
+            stage -= sa;
+            phase ^= 1;
+          }
+          if (++bs == sb) {
             bs = 0;
             bphase ^= 1;
           }
         }
       }
-      // accumulators this super-tile never touched: consume their hand-off too, so that no acc_empty
-      // barrier is ever more than one phase ahead of this warp
-      for (int t = 0; t < g.T; ++t)
-        if (!((started >> t) & 1u)) mbar_wait(&acc_empty[a0 + t], eparity, g.err, 3);
       if (elect_one()) umma_commit(&acc_full[set]);
       __syncwarp();
       PROF_ADD(3);
       pacc[14] += 1;  // super-tiles
     }
-    pacc[12] = clock64() - cta_t0;  // lifetime of the MMA role of this CTA
+    if (DBG) pacc[12] = clock64() - cta_t0;  // lifetime of the MMA role of this CTA
   } else {
     // ===================================================================== epilogue (warps 0..3)
     const float scale = g.out_scale ? g.out_scale[0] : 1.f;
@@ -615,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
-                if (srow[j] >= 0 && !(g.dbg & 32))  // dbg 32: experiment without the result stores
+                if (srow[j] >= 0 && !(dbg & 32))  // dbg 32: experiment without the result stores
                   *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
               }
               __syncwarp();
@@ -651,6 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
     }
   }
   if (warp == kProdWarp0) PROF_FLUSH(0, 1);
+  if (warp == kProdWarp0) PROF_FLUSH(15, 15);
   if (warp == kBWarp) PROF_FLUSH(2, 2);
   if (warp == kMmaWarp) PROF_FLUSH(3, 7);
   if (warp == kMmaWarp) PROF_FLUSH(10, 14);  // 11 = schedule hand-out + super-tile prologue of the MMA warp
@@ -1026,7 +1044,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   // the TMA load of the next panel cannot start before the MMAs of the current one retire: the 256-channel
   // layers waited 22 % of the time for weights); the rest of the budget goes to operand (gather) stages.
   // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments;
-  // LIDOG_G2_OPT bits: 1 = batched waits of the MMA warp, 2 = deep panel ring, 4 = L2 row prefetch (see k_gemm2).
+  // LIDOG_G2_OPT bits: 2 = deep panel ring, 4 = L2 row prefetch (see k_gemm2).
   int opt = 3;
   {
     const char* e = getenv("LIDOG_G2_OPT");
@@ -1063,8 +1081,12 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     g.pc = pc;
     g.n_panels = n_chunks / pc;
   }
-  g.bmax = (opt & 1) ? (g.sa < 4 ? g.sa : 4) : 1;
+  g.bmax = 0;  // (unused since the MMA warp takes all units of an (offset, panel) step together)
   g.pf = (opt & 4) ? 1 : 0;
+  if (g.T > g.sa) {  // the MMA warp waits for up to T stages at once: they must all fit in the ring
+    g.T = g.sa;
+    g.n_super = ceil_div(g.n_tiles, g.T);
+  }
   // Ring-phase rule: a producer warp revisits a stage only after the consumer freed it once, which the
   // parity wait can tell only when consecutive units of one warp are < one ring wrap apart: np <= sa.
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
@@ -1077,9 +1099,27 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   memset(&tmB, 0, sizeof(tmB));
   rc = tc_make_tmap(&tmB, B16, (int64_t)plan->kernel_volume * N, Ck, g.n_blk);
   if (rc) return rc;
-  LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(g.n_super < sm_count ? g.n_super : sm_count), (unsigned)n_split);
-  k_gemm2<<<grid, kThreads, smem, stream>>>(g, tmB);
+  // production instantiation unless an experiment switch is set; one instantiation per stage width
+#define LG_LAUNCH_GEMM2(DBGV, PCV)                                                                                   \
+  do {                                                                                                                \
+    LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2<DBGV, PCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_gemm2<DBGV, PCV><<<grid, kThreads, smem, stream>>>(g, tmB);                                                     \
+  } while (0)
+#define LG_LAUNCH_GEMM2_PC(DBGV)                                                                                      \
+  switch (g.pc) {                                                                                                     \
+    case 1: LG_LAUNCH_GEMM2(DBGV, 1); break;                                                                          \
+    case 2: LG_LAUNCH_GEMM2(DBGV, 2); break;                                                                          \
+    case 3: LG_LAUNCH_GEMM2(DBGV, 3); break;                                                                          \
+    default: LG_LAUNCH_GEMM2(DBGV, 4); break;                                                                         \
+  }
+  if (g.dbg) {
+    LG_LAUNCH_GEMM2_PC(true)
+  } else {
+    LG_LAUNCH_GEMM2_PC(false)
+  }
+#undef LG_LAUNCH_GEMM2_PC
+#undef LG_LAUNCH_GEMM2
   LG_LAUNCH_OK();
   return LG_OK;
 }
@@ -1172,3 +1212,8 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
 
 // experiment hook (not part of the reference-facing ABI): per-role wait cycles of CTA 0, LIDOG_DBG & 8
 extern "C" int lg_debug_profile(long long* out16, int reset) { return lg::debug_profile(out16, reset); }
+// event trace of CTA 0 (LIDOG_DBG & 8): out[5][512] clock64 values, see g_trace
+extern "C" int lg_debug_trace(long long* out) {
+  if (cudaMemcpyFromSymbol(out, lg::v2::g_trace, sizeof(long long) * 5 * lg::v2::kTraceUnits) != cudaSuccess) return LG_ERR_CUDA;
+  return LG_OK;
+}

@@ -80,15 +80,16 @@ def test_training_step_matches_oracle(cuda, mode, tol):
         return float((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm().clamp_min(1e-30))
 
     ref_params = dict(ref_net.named_parameters())
-    worst, worst_name = 0.0, None
+    top = max(float(p.grad.norm()) for p in ref_params.values())
+    bad = []
     for name, p in net.named_parameters():
         g, go = p.grad, ref_params[name].grad
         assert g is not None and go is not None and torch.isfinite(g).all(), name
-        if float(go.norm()) > 1e-10:
+        if float(go.norm()) > 1e-6 * top:  # gradients that are zero up to rounding (e.g. a bias in front of a BN) carry no signal
             e = rel(g, go)
-            if e > worst:
-                worst, worst_name = e, name
-    assert worst <= 20 * tol, (worst_name, worst)
+            if e > 20 * tol:
+                bad.append((name, e, float(go.norm()), float(g.norm())))
+    assert not bad, (top, bad[:8])
     # Adam moved the weights (|update| ~ lr on the first step) and nothing blew up
     moved = 0.0
     for name, p in net.named_parameters():

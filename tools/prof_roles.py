@@ -11,7 +11,7 @@ scans = synth.make_batch(8, 1234, "kitti", 7)
 q = ME.utils.sparse_quantize_batch([torch.from_numpy(p).to(dev) for p, _ in scans], [torch.from_numpy(l).to(dev) for _, l in scans], 0.05, -1)
 cm = ME.CoordinateManager.from_quantized(q)
 L = cabi.lib(); raw = C.CDLL(cabi.LIB_PATH)
-names = ["prodA wait empty", "prodA issue", "prodB wait empty", "mma wait acc_empty", "mma wait fullB", "mma wait fullA", "mma issue+commit", "mma loop ovh", "epi wait acc_full", "epi store", "mma fences", "mma sched+prologue", "MMA ROLE LIFETIME", "units (CTA 0)", "super-tiles (CTA 0)"]
+names = ["prodA wait empty", "prodA issue", "prodB wait empty", "mma wait acc_empty", "mma wait fullB", "mma wait fullA", "mma issue+commit", "mma loop ovh", "epi wait acc_full", "epi store", "mma fences", "mma sched+prologue", "MMA ROLE LIFETIME", "units (CTA 0)", "super-tiles (CTA 0)", "prodA wait ids"]
 for ts, cin, cout in ((1, 96, 96), (1, 32, 32), (8, 256, 256), (16, 256, 256)):
     layer = ME.MinkowskiConvolution(cin, cout, kernel_size=3, dimension=3)
     _, (pf, _, _, _) = layer._plans(cm, ts)
