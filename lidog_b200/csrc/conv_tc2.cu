@@ -141,11 +141,15 @@ __device__ __forceinline__ uint32_t offset_bits(TileMasks& tm, const lgConvPlan&
 }
 // Every role walks the same (offset k, tile bits m) sequence: set bits only -- the one-thread roles used to spend
 // ~100 cycles per ABSENT offset on the shift/or chains of a plain k = 0..K-1 scan.
+// Lane j of the warp computes the tile bits of offset 32 w + j once per mask word (the 32 shift/or instructions of
+// present_bits run in parallel across the lanes); inside the walk an offset's bits are one shuffle away.
 #define LG_FOR_EACH_OFFSET(tm, plan, tile0, nt, k, m)                                                  \
   for (int _w = 0; _w < (plan).mask_words; ++_w)                                                       \
-    for (uint32_t _kb = offset_bits(tm, plan, tile0, nt, _w); _kb; _kb &= _kb - 1)                     \
-      if (const int k = 32 * _w + __ffs(_kb) - 1; true)                                                \
-        if (const uint32_t m = present_bits(tm, k); true)
+    for (uint32_t _kb = offset_bits(tm, plan, tile0, nt, _w), _mk = present_bits(tm, lane); _kb;       \
+         _kb &= _kb - 1)                                                                               \
+      if (const int _j = __ffs(_kb) - 1; true)                                                         \
+        if (const int k = 32 * _w + _j; true)                                                          \
+          if (const uint32_t m = __shfl_sync(0xffffffffu, _mk, _j); true)
 
 __device__ __forceinline__ uint32_t any_mask(const lgConvPlan& p, int64_t tile0, int nt) {
   uint32_t m = 0;
