@@ -58,10 +58,12 @@ constexpr int kProdWarp0 = 6;
 constexpr int kProdWarps = 4;        // warps 6..9
 constexpr int kIdxWarp = kProdWarp0 + kProdWarps;  // warp 10: row-id ring (bulk copies of 512 B id rows)
 constexpr int kThreads = (kIdxWarp + 1) * 32;
+constexpr int kMma2Warp = kIdxWarp + 1;              // k_gemm2 only: second MMA issuer (SPLIT != 0)
+constexpr int kThreadsG2 = (kMma2Warp + 1) * 32;
 constexpr int kIdxSlotBytes = LG_TILE_ROWS * 4;
 constexpr int kSchedSlots = 4;                                   // super-tile hand-out ring
 constexpr int kSchedWords = 12;  // ring entry: [0] super-tile, [1] "tile has any offset" bits, [2..9] mask word 0 of its tiles
-constexpr int kSchedConsumers = kEpiWarps + 2 + kProdWarps;      // warps that read every ring entry
+constexpr int kSchedConsumers = kEpiWarps + 2 + kProdWarps;      // warps that read every ring entry (+1 with two issuers)
 constexpr int kStgPitch = 36;                                    // floats per staged row (32 + 4: conflict-free v4)
 constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;        // epilogue transposition buffers
 
@@ -221,8 +223,12 @@ struct Gemm2Args {
 };
 
 // DBG: instrumentation + experiment switches compiled in.  PC: 32-channel chunks per operand stage (= g.pc).
-template <bool DBG, int PC>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const __grid_constant__ CUtensorMap tmB) {
+// SPLIT: MMA issuers.  The one-thread MMA role sets the pace of the kernel (section 4.1 of DESIGN.md), so two
+// warps share it in a way that leaves every accumulator with ONE issuer (deterministic accumulation order):
+//   0 = one issuer; 1 = by tile parity (super-tiles of T >= 2 tiles: warp j issues the units of tiles t = j mod 2);
+//   2 = by column halves (T = 1: both warps issue every unit, warp j the MMAs of columns [j N/2, (j+1) N/2)).
+template <bool DBG, int PC, int SPLIT>
+__global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,29 +254,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
   const int n0 = blockIdx.y * g.n_blk;
   const int K = g.plan.kernel_volume;
   const int dbg = DBG ? g.dbg : 0;  // experiment switches fold away in the production instantiation
-  const bool prof = DBG && (dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  const bool prof = DBG && (dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp != kMma2Warp;
   long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long cta_t0 = DBG ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.sa; ++s) {
       mbar_init(&fullA[s], 32);
-      mbar_init(&emptyA[s], 1);
+      mbar_init(&emptyA[s], SPLIT == 2 ? 2 : 1);  // column split: both issuers read the stage
     }
     for (int s = 0; s < g.sb; ++s) {
       mbar_init(&fullB[s], 1);
-      mbar_init(&emptyB[s], 1);
+      mbar_init(&emptyB[s], SPLIT ? 2 : 1);  // every issuer releases the weight panel
     }
     for (int s = 0; s < ni; ++s) {
       mbar_init(&fullI[s], 1);
       mbar_init(&emptyI[s], 1);
     }
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_full[0], SPLIT ? 2 : 1);
+    mbar_init(&acc_full[1], SPLIT ? 2 : 1);
     for (int t = 0; t < 8; ++t) mbar_init(&acc_empty[t], kEpiWarps * 32);
     for (int t = 0; t < kSchedSlots; ++t) {
       mbar_init(&fullS[t], 1);
-      mbar_init(&emptyS[t], kSchedConsumers);
+      mbar_init(&emptyS[t], kSchedConsumers + (SPLIT ? 1 : 0));
     }
     fence_barrier_init();
   }
@@ -459,20 +465,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer
+  } else if (warp == kMmaWarp || warp == kMma2Warp) {
+    // ===================================================================== MMA issuer(s)
+    const int mw = (warp == kMmaWarp) ? 0 : 1;  // issuer index
+    if (SPLIT == 0 && mw) goto role_done;         // single-issuer instantiation: the extra warp has no role
     // The loop runs warp-uniformly (every lane computes the same unit sequence; the masks are broadcast), and
     // one elected lane issues the tcgen05 instructions: descriptors are a constant high word plus
     // (address >> 4) held in uniform registers, so a unit costs two barrier waits, a proxy fence and 2*pc
     // back-to-back UTCHMMAs.  Accumulators are handed back by the epilogue tile by tile (acc_empty[t]), so
     // the first offsets of the next super-tile overlap the drain of the previous one.
-    const uint32_t idesc = make_idesc(g.umma_fmt, 0, 0, LG_TILE_ROWS, g.n_blk);
+    // column split: this issuer's MMAs cover n_mma = N/2 columns starting at column col0 (weight rows col0..)
+    const int n_mma = (SPLIT == 2) ? g.n_blk / 2 : g.n_blk;
+    const uint32_t col0 = (SPLIT == 2 && mw) ? (uint32_t)(g.n_blk / 2) : 0u;
+    const uint32_t idesc = make_idesc(g.umma_fmt, 0, 0, LG_TILE_ROWS, n_mma);
     const uint64_t desc_hi = make_smem_desc(0, 16, 8 * kRowB, kLayoutSw64);
-    const uint32_t a_base = smem_u32(smA) >> 4, b_base = smem_u32(smB) >> 4;
+    const uint32_t a_base = smem_u32(smA) >> 4, b_base = (smem_u32(smB) + col0 * kRowB) >> 4;
     const uint32_t a_stage16 = (uint32_t)stageA >> 4, b_stage16 = (uint32_t)stageB >> 4;
     const uint32_t b_sub16 = (uint32_t)(g.n_blk * kRowB) >> 4;
     // everything the loop needs lives in registers: no parameter loads, no 64-bit index arithmetic in the hot path
     const int sa = g.sa, sb = g.sb, T = g.T, n_panels = g.n_panels, n_blk = g.n_blk, two_sets = g.sets == 2;
+    const uint32_t mine_bits = (SPLIT == 1) ? (mw ? 0xAAAAAAAAu : 0x55555555u) : 0xFFFFFFFFu;  // tiles this issuer owns
     int stage = 0, bs = 0, munit = 0;
     uint32_t phase = 0, bphase = 0, it = 0;
     SchedItem item;
@@ -502,12 +514,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
           const uint32_t db_lo = b_base + bs * b_stage16;
           // The units of this (offset, panel) -- at most T <= ring depth (host-checked) -- are handled together:
           // wait for their stages, ONE proxy fence, issue their MMAs back to back, release the stages.
+          const uint32_t mym = m & mine_bits;  // the units of this step that this issuer handles
           {
             int s = stage;
             uint32_t ph = phase;
             for (uint32_t bb = m; bb; bb &= bb - 1) {
-              mbar_wait(&fullA[s], ph, g.err, 5);
-              TRACE(2, munit + __popc(m & ~bb));
+              if (SPLIT != 1 || ((bb & (0u - bb)) & mym)) {
+                mbar_wait(&fullA[s], ph, g.err, 5);
+                TRACE(2, munit + __popc(m & ~bb));
+              }
               if (++s == sa) {
                 s = 0;
                 ph ^= 1;
@@ -522,9 +537,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             int s = stage;
             for (uint32_t bb = m; bb; bb &= bb - 1) {
               const int t = __ffs(bb) - 1;
+              if (SPLIT == 1 && !((mym >> t) & 1u)) {  // the other issuer's unit: only the stage counter moves
+                if (++s == sa) s = 0;
+                continue;
+              }
               const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
               const uint64_t db0 = desc_hi | (uint64_t)db_lo;
-              const uint32_t d_tmem = d_base + (uint32_t)t * (uint32_t)n_blk;
+              const uint32_t d_tmem = d_base + (uint32_t)t * (uint32_t)n_blk + col0;
               const uint32_t acc0 = (started >> t) & 1u;
               if (!(dbg & 4)) {
 #pragma unroll
@@ -551,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
             pacc[13] += __popc(m);  // units
           }
           PROF_ADD(6);
-          started |= m;
+          started |= mym;
           stage += __popc(m);
           if (stage >= sa) {
             stage -= sa;
@@ -671,6 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm2(const Gemm2Args g, const 
       if (warp == 0) PROF_ADD(9);
     }
   }
+role_done:
   if (warp == kProdWarp0) PROF_FLUSH(0, 1);
   if (warp == kProdWarp0) PROF_FLUSH(15, 15);
   if (warp == kBWarp) PROF_FLUSH(2, 2);
@@ -1105,17 +1125,29 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   if (rc) return rc;
   dim3 grid((unsigned)(g.n_super < sm_count ? g.n_super : sm_count), (unsigned)n_split);
   // production instantiation unless an experiment switch is set; one instantiation per stage width
-#define LG_LAUNCH_GEMM2(DBGV, PCV)                                                                                   \
-  do {                                                                                                                \
-    LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2<DBGV, PCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_gemm2<DBGV, PCV><<<grid, kThreads, smem, stream>>>(g, tmB);                                                     \
+  // issuers: tile-parity split for super-tiles of >= 2 tiles, column halves for single tiles (LIDOG_G2_MMA2=0: one)
+  int split = g.T >= 2 ? 1 : ((g.n_blk % 32 == 0) ? 2 : 0);
+  {
+    const char* e = getenv("LIDOG_G2_MMA2");
+    if (e && atoi(e) == 0) split = 0;
+  }
+#define LG_LAUNCH_GEMM2(DBGV, PCV, SPV)                                                                                   \
+  do {                                                                                                                     \
+    LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2<DBGV, PCV, SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_gemm2<DBGV, PCV, SPV><<<grid, kThreadsG2, smem, stream>>>(g, tmB);                                                   \
   } while (0)
-#define LG_LAUNCH_GEMM2_PC(DBGV)                                                                                      \
-  switch (g.pc) {                                                                                                     \
-    case 1: LG_LAUNCH_GEMM2(DBGV, 1); break;                                                                          \
-    case 2: LG_LAUNCH_GEMM2(DBGV, 2); break;                                                                          \
-    case 3: LG_LAUNCH_GEMM2(DBGV, 3); break;                                                                          \
-    default: LG_LAUNCH_GEMM2(DBGV, 4); break;                                                                         \
+#define LG_LAUNCH_GEMM2_SP(DBGV, PCV)                                                                                      \
+  switch (split) {                                                                                                         \
+    case 0: LG_LAUNCH_GEMM2(DBGV, PCV, 0); break;                                                                          \
+    case 1: LG_LAUNCH_GEMM2(DBGV, PCV, 1); break;                                                                          \
+    default: LG_LAUNCH_GEMM2(DBGV, PCV, 2); break;                                                                         \
+  }
+#define LG_LAUNCH_GEMM2_PC(DBGV)                                                                                           \
+  switch (g.pc) {                                                                                                          \
+    case 1: LG_LAUNCH_GEMM2_SP(DBGV, 1); break;                                                                            \
+    case 2: LG_LAUNCH_GEMM2_SP(DBGV, 2); break;                                                                            \
+    case 3: LG_LAUNCH_GEMM2_SP(DBGV, 3); break;                                                                            \
+    default: LG_LAUNCH_GEMM2_SP(DBGV, 4); break;                                                                           \
   }
   if (g.dbg) {
     LG_LAUNCH_GEMM2_PC(true)
@@ -1123,6 +1155,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     LG_LAUNCH_GEMM2_PC(false)
   }
 #undef LG_LAUNCH_GEMM2_PC
+#undef LG_LAUNCH_GEMM2_SP
 #undef LG_LAUNCH_GEMM2
   LG_LAUNCH_OK();
   return LG_OK;
