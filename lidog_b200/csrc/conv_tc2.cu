@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
         }
       }
     }
-  } else if (warp >= kProdWarp0) {
+  } else if (warp >= kProdWarp0 && warp < kProdWarp0 + kProdWarps) {
     // ===================================================================== A producers (cp.async gather)
     const int pw = warp - kProdWarp0;
     int stage = 0, turn = 0, slot = 0, punit = 0;
@@ -1125,11 +1125,15 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   if (rc) return rc;
   dim3 grid((unsigned)(g.n_super < sm_count ? g.n_super : sm_count), (unsigned)n_split);
   // production instantiation unless an experiment switch is set; one instantiation per stage width
-  // issuers: tile-parity split for super-tiles of >= 2 tiles, column halves for single tiles (LIDOG_G2_MMA2=0: one)
-  int split = g.T >= 2 ? 1 : ((g.n_blk % 32 == 0) ? 2 : 0);
+  // Issuers.  EXPERIMENTAL, off by default (LIDOG_G2_MMA2=1 enables it): tile-parity split for super-tiles of >= 2
+  // tiles, column halves for single tiles.  Measured on B200 after the MMA role was trimmed
+  // (profiles/r01_s4_sweep_h4_two_issuers.txt): -6 % on ts4 128->128, -4 % on ts4 64->64, nothing on the
+  // 256-channel layers -- the issuer is no longer what the kernel waits for -- and the tile-parity mode still
+  // traps on the ts2 96->96 shape (unresolved).  The single-issuer instantiation is the verified product path.
+  int split = 0;
   {
     const char* e = getenv("LIDOG_G2_MMA2");
-    if (e && atoi(e) == 0) split = 0;
+    if (e && atoi(e) != 0) split = g.T >= 2 ? 1 : ((g.n_blk % 32 == 0) ? 2 : 0);
   }
 #define LG_LAUNCH_GEMM2(DBGV, PCV, SPV)                                                                                   \
   do {                                                                                                                     \
