@@ -30,7 +30,7 @@ def bev_label_image(coords4: torch.Tensor, colabels: torch.Tensor, batch_size: i
     # torch's CUDA kernel for `tensor / python_scalar` multiplies by the reciprocal; the reference divides (numpy
     # float32, IEEE), and floor() of the two differs on cell boundaries -- divide by a TENSOR to get the true quotient
     # (found by tests/test_gpu_trainer.py against the CPU evaluation of this same function)
-    grid_t = torch.tensor(grid, dtype=torch.float32, device=dev)
+    grid_t = torch.full((), grid, dtype=torch.float32, device=dev)  # (a fill kernel: no host-to-device copy / sync)
     px = torch.floor(torch.div(pts[:, 0] - (-bound), grid_t)).long()
     py = torch.floor(img - torch.div(pts[:, 1] - (-bound), grid_t)).long() - 1
     py = torch.where(py < 0, py + img, py)

@@ -102,8 +102,9 @@ def sparse_quantize_batch(points_list, labels_list, quantization_size, ignore_la
     dev = points_list[0].device
     sizes = [p.shape[0] for p in points_list]
     pts = torch.cat(points_list, 0)
-    b = torch.repeat_interleave(torch.arange(len(sizes), device=dev, dtype=torch.int32),
-                                torch.tensor(sizes, device=dev))
+    # batch index per point, built from fill kernels: torch.tensor(sizes, device=...) is a synchronous host-to-device
+    # copy, i.e. a full stream sync at the start of every step (tools/host_profile.py)
+    b = torch.cat([torch.full((n,), i, dtype=torch.int32, device=dev) for i, n in enumerate(sizes)], 0)
     q4 = quantize_points(pts, quantization_size, b)
     lab = None if labels_list is None else torch.cat(labels_list, 0)
     res = coords_unique(q4, 1, labels=lab, ignore_label=ignore_label)
