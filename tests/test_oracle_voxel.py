@@ -115,3 +115,23 @@ def test_bev_label_image_matches_numpy_restatement():
         got = bev_label_image(c4, torch.from_numpy(colab), 1, cfg["bound"], cfg["bev_img"])
         assert got.shape == (1, cfg["bev_img"], cfg["bev_img"])
         assert np.array_equal(got[0].numpy(), want)
+
+
+def test_mix3d_shaped_sample_requantises_through_float32():
+    """Mix3D-shaped synthetic samples (lidog_b200/lidog/synth.py, reference utils/datasets/mix3D.py:43-87): the
+    merged cloud is metric float32 voxel corners of two scans; re-quantising it does NOT give back the union of
+    the two integer voxel sets (float32(c * 0.05) / 0.05 floors to c - 1 for some c), and the oracle reproduces
+    numpy's float32 arithmetic exactly."""
+    from lidog_b200.lidog import synth
+    pts, lab = synth.make_scan(21, "mix3d")
+    assert pts.dtype == np.float32 and lab.dtype == np.int32 and len(pts) == len(lab)
+    q, _, _, umap, inv = ov.sparse_quantize(pts, np.ones((len(pts), 1), np.float32), lab, -1, True, True, False, 0.05)
+    want = np.floor(pts / np.float32(0.05)).astype(np.int32)
+    assert np.array_equal(q[inv], want) and np.array_equal(want[umap], q)
+    # the two sources, quantised on their own
+    srcs = [synth._quantize_first(*synth.make_scan(21 + 5003 * j, "kitti"), 0.05)[0] for j in range(2)]
+    union = np.unique(np.concatenate(srcs), axis=0)
+    merged = np.unique(q, axis=0)
+    assert len(merged) != len(union) or not np.array_equal(merged, union)  # the requantisation trap is real
+    again, _ = synth.make_scan(21, "mix3d")
+    assert np.array_equal(again, pts)  # deterministic
