@@ -213,6 +213,7 @@ struct Gemm2Args {
             // 32 = no result stores, 64 = no row-id copies, 128 = stage release by plain arrive (only with 4);
             // 8 = per-role cycle counters of CTA 0
   int T, pc, n_panels, sa, sb, np;  // np = active producer warps (<= sa, see the ring-phase note)
+  int ni;                           // row-id ring slots (a multiple of np)
   int pf;                           // id warp prefetches the operand rows of upcoming units into L2
   int bmax;                         // units the MMA warp waits for together (one proxy fence per batch), <= sa
   int sets;                         // accumulator sets in TMEM (sets * T * n_blk <= 512): 2 = the epilogue of one
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
   uint8_t* smA = smem;
   uint8_t* smB = smem + (size_t)g.sa * stageA;
   uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
-  const int ni = 8 * g.np;
+  const int ni = g.ni;
   float* smStg = (float*)(smI + (size_t)ni * kIdxSlotBytes);  // epilogue transposition buffers
   uint64_t* fullA = (uint64_t*)((uint8_t*)smStg + kStgBytes);
   uint64_t* emptyA = fullA + g.sa;
@@ -977,8 +978,7 @@ static inline size_t wgrad_tail_bytes(int sa, int sb) {  // id ring + barriers +
   const int ni = 8 * kProdWarps;
   return (size_t)ni * kIdxSlotBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 2) * 8 + 16 + 1024;
 }
-static inline size_t tail_bytes(int sa, int sb) {  // + epilogue staging + schedule ring
-  const int ni = 8 * kProdWarps;
+static inline size_t tail_bytes(int sa, int sb, int ni = 8 * kProdWarps) {  // + epilogue staging + schedule ring
   return (size_t)ni * kIdxSlotBytes + kStgBytes + (size_t)(2 * sa + 2 * sb + 2 * ni + 11 + 2 * kSchedSlots) * 8 + 16 +
          4 * kSchedWords * kSchedSlots + 1024;
 }
@@ -1087,17 +1087,36 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     g.pc = pc;
     g.n_panels = n_chunks / pc;
   }
+  // LIDOG_G2_RING=0 restores the ring shape of the first validated lean kernel (32 id slots, 3 weight stages when
+  // they fit).  Default: the ncu source view of the lean kernel (profiles/r01_s4_gemm2_source_stalls.txt) shows the
+  // MMA warp polling the stage-full barrier ~17 times per unit and the producers waiting for free stages a quarter
+  // of the time -- a latency-bound ring -- so shared memory goes to operand stages first: 16 id slots (8 KB instead
+  // of 16) and 2 weight stages whenever that buys another operand stage.
+  static int ring_new = -1;
+  if (ring_new < 0) {
+    const char* e = getenv("LIDOG_G2_RING");
+    ring_new = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int ni_slots = ring_new ? 4 * kProdWarps : 8 * kProdWarps;
   size_t stageA, stageB;
   for (;;) {
     stageA = (size_t)g.pc * kSub, stageB = (size_t)g.pc * g.n_blk * kRowB;
     if (force_sb >= 2)
       g.sb = force_sb;
     else if (opt & 2)
-      g.sb = (3 * stageB + 4 * stageA + tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
+      g.sb = (3 * stageB + 4 * stageA + tail_bytes(4, 3, ni_slots) <= kSmemBudget) ? 3 : 2;
     else
       g.sb = (3 * stageB <= 80 * 1024) ? 3 : 2;
     g.sa = 12;
-    while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
+    while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb, ni_slots) > kSmemBudget) --g.sa;
+    if (ring_new && force_sb < 2 && g.sb == 3 && g.sa < 12) {  // would 2 weight stages buy an operand stage?
+      int sa2 = 12;
+      while (sa2 > 2 && sa2 * stageA + 2 * stageB + tail_bytes(sa2, 2, ni_slots) > kSmemBudget) --sa2;
+      if (sa2 > g.sa) {
+        g.sa = sa2;
+        g.sb = 2;
+      }
+    }
     if (g.sa >= kProdWarps || g.pc == 1) break;
     // deeper ring with smaller panels (pc must divide the chunk count)
     int pc = g.pc - 1;
@@ -1114,7 +1133,8 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   // Ring-phase rule: a producer warp revisits a stage only after the consumer freed it once, which the
   // parity wait can tell only when consecutive units of one warp are < one ring wrap apart: np <= sa.
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
-  const size_t smem = g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb);
+  g.ni = ni_slots;
+  const size_t smem = g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb, ni_slots);
   if (smem > kSmemBudget) {
     set_error("lg_conv_gemm_tc: shared memory %zu exceeds the budget (Ck=%d N=%d)", smem, Ck, N);
     return LG_ERR_UNSUPPORTED;
