@@ -1109,7 +1109,10 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
       g.sb = (3 * stageB <= 80 * 1024) ? 3 : 2;
     g.sa = 12;
     while (g.sa > 2 && g.sa * stageA + g.sb * stageB + tail_bytes(g.sa, g.sb, ni_slots) > kSmemBudget) --g.sa;
-    if (ring_new && force_sb < 2 && g.sb == 3 && g.sa < 12) {  // would 2 weight stages buy an operand stage?
+    // would 2 weight stages buy an operand stage?  Only where a weight stage is no bigger than an operand stage:
+    // measured (profiles/r01_s4_sweep_n_ring.txt) -17 % / -12 % on the 128-channel layers at tensor stride 8 / 4,
+    // but +2 ... +5 % on the 256-channel single-tile layers, whose 32 KB panels want the third stage.
+    if (ring_new && force_sb < 2 && g.sb == 3 && g.sa < 12 && stageB <= stageA) {
       int sa2 = 12;
       while (sa2 > 2 && sa2 * stageA + 2 * stageB + tail_bytes(sa2, 2, ni_slots) > kSmemBudget) --sa2;
       if (sa2 > g.sa) {
