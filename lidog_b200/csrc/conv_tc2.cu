@@ -520,10 +520,12 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
             int s = stage;
             uint32_t ph = phase;
             for (uint32_t bb = m; bb; bb &= bb - 1) {
-              if (SPLIT != 1 || ((bb & (0u - bb)) & mym)) {
-                mbar_wait(&fullA[s], ph, g.err, 5);
-                TRACE(2, munit + __popc(m & ~bb));
-              }
+              // Every issuer observes EVERY phase of every stage barrier, also for the units it does not issue: a
+              // parity wait cannot tell phase n from phase n + 2, and an issuer that skipped the other issuer's
+              // phase and ran >= one ring wrap ahead took the stale completion of its own previous use for the
+              // new one (this is what trapped the tile-parity mode on the 5-stage 96->96 shape).
+              mbar_wait(&fullA[s], ph, g.err, 5);
+              TRACE(2, munit + __popc(m & ~bb));
               if (++s == sa) {
                 s = 0;
                 ph ^= 1;
@@ -1151,8 +1153,10 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   // Issuers.  EXPERIMENTAL, off by default (LIDOG_G2_MMA2=1 enables it): tile-parity split for super-tiles of >= 2
   // tiles, column halves for single tiles.  Measured on B200 after the MMA role was trimmed
   // (profiles/r01_s4_sweep_h4_two_issuers.txt): -6 % on ts4 128->128, -4 % on ts4 64->64, nothing on the
-  // 256-channel layers -- the issuer is no longer what the kernel waits for -- and the tile-parity mode still
-  // traps on the ts2 96->96 shape (unresolved).  The single-issuer instantiation is the verified product path.
+  // 256-channel layers -- the issuer is no longer what the kernel waits for.  The tile-parity mode trapped on the
+  // ts2 96->96 shape (5-stage ring): an issuer that skipped the other issuer's barrier phases could alias parities
+  // once it ran a ring wrap ahead; the waits now cover every phase (fix written after the GPU budget of the round
+  // was spent: NOT yet re-verified on hardware).  The single-issuer instantiation is the verified product path.
   int split = 0;
   {
     const char* e = getenv("LIDOG_G2_MMA2");
