@@ -61,6 +61,12 @@ size_t lg_hash_bytes(int64_t capacity);
 int lg_quantize_points(const float* points_xyz, const int32_t* batch_of_row, int64_t n, float size_x, float size_y,
                        float size_z, int32_t* coords4_out, void* stream);
 
+/* The same for float64 points, divided in float64: what the reference's TRAINING path feeds sparse_quantize -- its
+ * augmentations multiply the float32 cloud by float64 matrices (utils/common/augmentation.py:10-20, applied at
+ * utils/datasets/semantickitti_bev.py:214-219), and numpy keeps `float64_array / python_float` in float64. */
+int lg_quantize_points_f64(const double* points_xyz, const int32_t* batch_of_row, int64_t n, double size_x,
+                           double size_y, double size_z, int32_t* coords4_out, void* stream);
+
 size_t lg_coords_unique_workspace(int64_t n);
 
 /* Unique coordinates in first-occurrence order + hash table build.

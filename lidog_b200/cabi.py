@@ -37,6 +37,7 @@ SIGNATURES = {
     "lg_hash_capacity": (_i64, [_i64]),
     "lg_hash_bytes": (_sz, [_i64]),
     "lg_quantize_points": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp]),
+    "lg_quantize_points_f64": (C.c_int, [_vp, _vp, _i64, C.c_double, C.c_double, C.c_double, _vp, _vp]),
     "lg_coords_unique_workspace": (_sz, [_i64]),
     "lg_coords_unique": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "lg_kernel_map": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
@@ -76,7 +77,7 @@ SIGNATURES = {
 # CUDA kernels launched by one call of each entry point (memsets not counted); bench.py multiplies
 # these by the call counts to report `gpu_launches`.
 KERNELS_PER_CALL = {
-    "lg_quantize_points": 1, "lg_coords_unique": 7, "lg_kernel_map": 1, "lg_kernel_map_sorted": 7, "lg_kernel_map_pairs": 3,
+    "lg_quantize_points": 1, "lg_quantize_points_f64": 1, "lg_coords_unique": 7, "lg_kernel_map": 1, "lg_kernel_map_sorted": 7, "lg_kernel_map_pairs": 3,
     "lg_kernel_map_up2": 9, "lg_conv_gemm_simt": 1, "lg_conv_wgrad_simt": 2, "lg_cast_rows": 1,
     "lg_absmax_scale": 2, "lg_prep_weights": 1, "lg_conv_gemm_tc": 1, "lg_conv_wgrad_tc": 2,
     "lg_bev_forward": 2, "lg_bev_backward": 3,

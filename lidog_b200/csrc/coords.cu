@@ -22,6 +22,21 @@ __global__ void __launch_bounds__(256)
   out[i] = make_int4(b, (int)x, (int)y, (int)z);
 }
 
+// float64 points: the reference's TRAINING path.  Its augmentations multiply the float32 cloud by float64 matrices
+// (utils/common/augmentation.py:10-20: `coords @ R` with R from scipy's expm), so sparse_quantize receives float64
+// and numpy divides in float64; floor(x / 0.05) differs between the two precisions on cell boundaries.
+__global__ void __launch_bounds__(256)
+    k_quantize_f64(const double* __restrict__ pts, const int32_t* __restrict__ batch_of_row, int64_t n, double sx,
+                   double sy, double sz, int4* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = floor(__ddiv_rn(pts[3 * i + 0], sx));
+  const double y = floor(__ddiv_rn(pts[3 * i + 1], sy));
+  const double z = floor(__ddiv_rn(pts[3 * i + 2], sz));
+  const int b = batch_of_row ? batch_of_row[i] : 0;
+  out[i] = make_int4(b, (int)x, (int)y, (int)z);
+}
+
 __device__ __forceinline__ int4 stride_coord(int4 c, int stride) {
   if (stride > 1) {
     c.y = floor_div(c.y, stride) * stride;
@@ -160,6 +175,17 @@ extern "C" int lg_quantize_points(const float* points_xyz, const int32_t* batch_
   LG_CHECK_ARG(points_xyz && coords4_out, "lg_quantize_points: null pointer");
   k_quantize<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(points_xyz, batch_of_row, n, size_x, size_y,
                                                                            size_z, (int4*)coords4_out);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+extern "C" int lg_quantize_points_f64(const double* points_xyz, const int32_t* batch_of_row, int64_t n, double size_x,
+                                      double size_y, double size_z, int32_t* coords4_out, void* stream) {
+  LG_CHECK_ARG(n >= 0 && size_x > 0 && size_y > 0 && size_z > 0, "lg_quantize_points_f64: bad n or voxel size");
+  if (n == 0) return LG_OK;
+  LG_CHECK_ARG(points_xyz && coords4_out, "lg_quantize_points_f64: null pointer");
+  k_quantize_f64<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(points_xyz, batch_of_row, n, size_x,
+                                                                               size_y, size_z, (int4*)coords4_out);
   LG_LAUNCH_OK();
   return LG_OK;
 }

@@ -24,18 +24,22 @@ def _device(device=None):
 
 
 def quantize_points(points: torch.Tensor, quantization_size, batch_of_row: torch.Tensor | None = None) -> torch.Tensor:
-    """float32 [N,3] device points -> int32 [N,4] (batch, floor(p / size)) on the device."""
+    """[N,3] device points -> int32 [N,4] (batch, floor(p / size)) on the device, in the precision numpy would use:
+    float64 points (the reference's augmented training clouds) divide in float64, everything else in float32."""
     assert points.is_cuda and points.dim() == 2 and points.shape[1] == 3
-    pts = points.to(torch.float32).contiguous()
+    f64 = points.dtype == torch.float64
+    pts = points.contiguous() if f64 else points.to(torch.float32).contiguous()
+    cast = float if f64 else (lambda v: float(np.float32(v)))
     if isinstance(quantization_size, (int, float)):
-        sx = sy = sz = float(np.float32(quantization_size))
+        sx = sy = sz = cast(quantization_size)
     else:
-        sx, sy, sz = (float(np.float32(v)) for v in quantization_size)
+        sx, sy, sz = (cast(v) for v in quantization_size)
     out = torch.empty((pts.shape[0], 4), dtype=torch.int32, device=pts.device)
     if batch_of_row is not None:
         batch_of_row = batch_of_row.to(device=pts.device, dtype=torch.int32).contiguous()
-    cabi.check(cabi.lib().lg_quantize_points(cabi.ptr(pts), cabi.ptr(batch_of_row), pts.shape[0], sx, sy, sz,
-                                             cabi.ptr(out), cabi.stream()), "lg_quantize_points")
+    L = cabi.lib()
+    fn, name = (L.lg_quantize_points_f64, "lg_quantize_points_f64") if f64 else (L.lg_quantize_points, "lg_quantize_points")
+    cabi.check(fn(cabi.ptr(pts), cabi.ptr(batch_of_row), pts.shape[0], sx, sy, sz, cabi.ptr(out), cabi.stream()), name)
     return out
 
 
@@ -60,7 +64,7 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, 
     c = torch.from_numpy(np.ascontiguousarray(coordinates)) if is_np else coordinates
     c = c.to(dev)
     if quantization_size is not None:
-        q4 = quantize_points(c.to(torch.float32), quantization_size)
+        q4 = quantize_points(c if c.dtype == torch.float64 else c.to(torch.float32), quantization_size)
     else:
         q4 = torch.zeros((c.shape[0], 4), dtype=torch.int32, device=dev)
         q4[:, 1:] = torch.floor(c).to(torch.int32) if c.is_floating_point() else c.to(torch.int32)

@@ -47,19 +47,23 @@ def unique_first_occurrence(coords: np.ndarray):
 
 
 def quantize_coords(points: np.ndarray, quantization_size) -> np.ndarray:
-    """q = int32(floor(points / size)) in float32 (App. C.1).
+    """q = int32(floor(points / size)) in float32 -- or float64 for float64 points (App. C.1).
 
     numpy keeps `float32_array / python_float` in float32, which is what the
     call site semantickitti_bev.py:232-238 feeds ME; a length-3 size is applied
     per axis (minkunet_bev.py:279-284).
     """
     p = np.asarray(points)
-    if p.dtype != np.float32:
-        p = p.astype(np.float32)
+    # float64 clouds (the reference's augmented training path: `coords @ R` with a float64 R,
+    # utils/common/augmentation.py:10-20) stay float64 -- numpy divides an array by a python float in the ARRAY's
+    # precision; every other dtype goes through float32 like the float32 clouds of the datasets
+    dt = np.float64 if p.dtype == np.float64 else np.float32
+    if p.dtype != dt:
+        p = p.astype(dt)
     if np.isscalar(quantization_size):
-        q = np.floor(p / np.float32(quantization_size))
+        q = np.floor(p / dt(quantization_size))
     else:
-        s = np.asarray(quantization_size, dtype=np.float32).reshape(1, -1)
+        s = np.asarray(quantization_size, dtype=dt).reshape(1, -1)
         q = np.floor(p / s)
     return q.astype(np.int32)
 

@@ -46,6 +46,38 @@ def test_sparse_quantize_variants(cuda):
     assert np.array_equal(um, ref[0]) and np.array_equal(inv, ref[1])
 
 
+def _augmented_cloud(seed, n=40000):
+    """A float64 cloud the way the reference's training path makes it: float32 points times a float64 rotation
+    and per-axis scales (utils/common/augmentation.py:10-44)."""
+    rng = np.random.default_rng(seed)
+    pts = random_surface_cloud(rng, n)
+    th = 0.3 * (rng.random() - 0.5)
+    R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+    out = pts @ R  # float32 @ float64 -> float64
+    out[:, 0] *= 0.95 + 0.1 * rng.random()
+    out[:, 1] *= 0.95 + 0.1 * rng.random()
+    assert out.dtype == np.float64
+    return out
+
+
+def test_sparse_quantize_float64_clouds_divide_in_float64(cuda):
+    """Augmented training clouds are float64 and numpy divides them in float64 (lg_quantize_points_f64); a float32
+    division of the same points lands in a different voxel for some of them."""
+    import MinkowskiEngine as ME
+    pts = _augmented_cloud(5)
+    labels = np.random.default_rng(6).integers(-1, 7, pts.shape[0]).astype(np.int32)
+    ref = ov.sparse_quantize(pts, None, labels, -1, True, True, False, 0.05)
+    got = ME.utils.sparse_quantize(pts, labels=labels, ignore_label=-1, quantization_size=0.05, return_index=True,
+                                   return_inverse=True)
+    for g, r, name in zip(got, ref, ("coords", "colabels", "unique_map", "inverse_map")):
+        assert np.array_equal(np.asarray(g), r), name
+    assert np.array_equal(got[0][got[3]], np.floor(pts / 0.05).astype(np.int32))
+    as32 = ME.utils.sparse_quantize(pts.astype(np.float32), quantization_size=0.05)
+    assert as32.shape != got[0].shape or not np.array_equal(as32, got[0])  # the precisions really differ here
+    t = ME.utils.sparse_quantize(torch.from_numpy(pts).to(cuda), quantization_size=0.05)  # device float64 tensor
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), ref[0])
+
+
 def test_mix3d_requantisation_trap(cuda):
     """floor(float32(c*0.05)/0.05) != c for some c (SURVEY 8a notes): GPU must follow the fp32 ops."""
     import MinkowskiEngine as ME

@@ -135,3 +135,19 @@ def test_mix3d_shaped_sample_requantises_through_float32():
     assert len(merged) != len(union) or not np.array_equal(merged, union)  # the requantisation trap is real
     again, _ = synth.make_scan(21, "mix3d")
     assert np.array_equal(again, pts)  # deterministic
+
+
+def test_quantize_keeps_float64_clouds_in_float64():
+    """numpy divides `float64_array / python_float` in float64 (the reference's augmented training clouds,
+    utils/common/augmentation.py:10-20) and `float32_array / python_float` in float32; the two floor differently on
+    cell boundaries, and the oracle follows the array's precision."""
+    rng = np.random.default_rng(3)
+    c = rng.integers(-1200, 1200, 30000)
+    p64 = np.stack([c * 0.05, c * 0.05 + 1e-9, c * 0.05 - 1e-9], 1)  # points on and next to cell boundaries
+    q64 = ov.quantize_coords(p64, 0.05)
+    assert np.array_equal(q64, np.floor(p64 / 0.05).astype(np.int32))
+    q32 = ov.quantize_coords(p64.astype(np.float32), 0.05)
+    assert np.array_equal(q32, np.floor(p64.astype(np.float32) / np.float32(0.05)).astype(np.int32))
+    assert (q64 != q32).any()
+    per_axis = ov.quantize_coords(p64, [0.3, 0.2, 1.0])
+    assert np.array_equal(per_axis, np.floor(p64 / np.array([0.3, 0.2, 1.0])).astype(np.int32))
