@@ -57,7 +57,9 @@ def _augmented_cloud(seed, n=40000):
     out[:, 0] *= 0.95 + 0.1 * rng.random()
     out[:, 1] *= 0.95 + 0.1 * rng.random()
     assert out.dtype == np.float64
-    return out
+    # plus points exactly on / next to voxel boundaries, where the two precisions are known to floor differently
+    c = rng.integers(-240, 240, (2000, 3))
+    return np.concatenate([out, c * 0.05, c * 0.05 + 1e-9], 0)
 
 
 def test_sparse_quantize_float64_clouds_divide_in_float64(cuda):
@@ -72,8 +74,8 @@ def test_sparse_quantize_float64_clouds_divide_in_float64(cuda):
     for g, r, name in zip(got, ref, ("coords", "colabels", "unique_map", "inverse_map")):
         assert np.array_equal(np.asarray(g), r), name
     assert np.array_equal(got[0][got[3]], np.floor(pts / 0.05).astype(np.int32))
-    as32 = ME.utils.sparse_quantize(pts.astype(np.float32), quantization_size=0.05)
-    assert as32.shape != got[0].shape or not np.array_equal(as32, got[0])  # the precisions really differ here
+    c32, inv32 = ME.utils.sparse_quantize(pts.astype(np.float32), quantization_size=0.05, return_inverse=True)
+    assert (c32[inv32] != got[0][got[3]]).any()  # per point: the precisions really differ on this cloud
     t = ME.utils.sparse_quantize(torch.from_numpy(pts).to(cuda), quantization_size=0.05)  # device float64 tensor
     assert t.is_cuda and np.array_equal(t.cpu().numpy(), ref[0])
 
