@@ -106,3 +106,35 @@ def test_model_state_dict_matches_reference_names():
             assert {k: tuple(v.shape) for k, v in r.state_dict().items()} == sd
         finally:
             sys.path.remove("/root/reference")
+
+
+def test_wgrad_workspace_covers_the_chunk_rule(libpath):
+    """`lg_conv_wgrad_tc_workspace` is host-only and must cover the partial-dW buffers of `k_wgrad2`:
+    chunks x K x Cin x Cout floats, chunks = tiles / 32 clamped to [one wave of 148 CTAs, four waves] over the
+    (offset group x 128-channel block) CTAs (csrc/conv_tc2.cu, from the CTA sweep in profiles/r01_s4_sweep_a.txt).
+    (The entry point returns the maximum over the kernel generations, so this is a lower bound.)"""
+    import math
+    import os
+    from lidog_b200 import cabi
+    os.environ.pop("LIDOG_WG_CTAS", None)
+    L = cabi.lib()
+
+    def workspace(n_tiles, K, cin, cout):
+        plan = cabi.ConvPlan(None, 128 * n_tiles, None, None, K, (K + 31) // 32, 128 * n_tiles, 128 * n_tiles,
+                             128 * n_tiles)
+        return L.lg_conv_wgrad_tc_workspace(plan, cin, cout)
+
+    def rule(n_tiles, K, cin, cout):
+        gmax = min(512 // cout, 8, K)
+        per = math.ceil(K / gmax) * math.ceil(cin / 128)
+        want = min(max(n_tiles // 32, math.ceil(148 / per)), max(592 // per, 1))
+        c = max(1, min(n_tiles, want))
+        return math.ceil(n_tiles / math.ceil(n_tiles / c))
+
+    for shape in [(5065, 27, 96, 96), (2463, 27, 96, 96), (964, 27, 128, 128), (353, 27, 256, 256),
+                  (129, 27, 256, 256), (353, 27, 128, 128), (964, 27, 64, 64), (5065, 8, 32, 32), (5065, 1, 128, 96),
+                  (3, 27, 384, 256)]:
+        n_tiles, K, cin, cout = shape
+        assert workspace(*shape) >= rule(*shape) * K * cin * cout * 4 + 256, shape
+    assert rule(129, 27, 256, 256) == 6 and rule(5065, 27, 96, 96) == 98  # the two ends of the sweep
+    assert workspace(0, 27, 96, 96) > 0 and L.lg_conv_wgrad_tc_workspace(None, 96, 96) == 0
