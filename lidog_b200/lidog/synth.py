@@ -150,3 +150,26 @@ def make_bev_labels(qcoords: np.ndarray, colabels: np.ndarray, bound: float, img
 def make_batch(batch_size: int, seed: int = 1234, shape: str = "kitti", num_classes: int = 7):
     """List of `batch_size` scans, a different scan per batch slot."""
     return [make_scan(seed + i, shape, num_classes) for i in range(batch_size)]
+
+
+def make_plane_cloud(n_points: int, seed: int = 0, extent: float = 40.0, planes: int = 12, noise: float = 0.01,
+                     num_classes: int = 7):
+    """Micro-benchmark cloud (BASELINE configs[3]): `n_points` points on a few random planes,
+    which keeps the 5-12 occupied neighbours per 0.05 m voxel that LiDAR surfaces have at any point count from
+    10 k to 2 M.  -> (points float32 [N,3], labels int32 [N]); the plane sizes grow with N so the point density per
+    voxel stays ~1-2."""
+    rng = np.random.default_rng(seed)
+    per = max(n_points // planes, 1)
+    # a plane of side L holds (L / 0.05)^2 voxels; aim at ~1.5 points per voxel
+    side = float(np.clip(0.05 * np.sqrt(per / 1.5), 1.0, extent))
+    pts, labs = [], []
+    for j in range(planes):
+        origin = rng.uniform(-extent / 2, extent / 2, 3)
+        u, v = rng.standard_normal(3), rng.standard_normal(3)
+        u /= np.linalg.norm(u)
+        v -= u * (u @ v)
+        v /= np.linalg.norm(v)
+        a, b = rng.uniform(-side / 2, side / 2, (2, per))
+        pts.append(origin + a[:, None] * u + b[:, None] * v + rng.normal(0.0, noise, (per, 3)))
+        labs.append(np.full(per, rng.integers(-1, num_classes), np.int32))
+    return np.concatenate(pts).astype(np.float32), np.concatenate(labs)

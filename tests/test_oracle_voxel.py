@@ -1,6 +1,7 @@
 """CPU: the oracle's voxelisation / coordinate-map / kernel-map conventions.
 MinkowskiEngine is absent, so these are property tests + hand-computed cases (parity unpinned)."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 from oracle import voxel as ov
@@ -151,3 +152,16 @@ def test_quantize_keeps_float64_clouds_in_float64():
     assert (q64 != q32).any()
     per_axis = ov.quantize_coords(p64, [0.3, 0.2, 1.0])
     assert np.array_equal(per_axis, np.floor(p64 / np.array([0.3, 0.2, 1.0])).astype(np.int32))
+
+
+@pytest.mark.parametrize("n", [10_000, 200_000])
+def test_plane_cloud_keeps_lidar_like_neighbourhoods(n):
+    """The micro-benchmark clouds (BASELINE configs[3]) keep 5-12 occupied neighbours per voxel at any size."""
+    from lidog_b200.lidog import synth
+    pts, lab = synth.make_plane_cloud(n, 3)
+    assert pts.dtype == np.float32 and lab.dtype == np.int32 and abs(len(pts) - n) < 12
+    q = np.unique(ov.quantize_coords(pts, 0.05), axis=0)
+    c4 = np.concatenate([np.zeros((len(q), 1), np.int32), q], 1)
+    pairs = sum(len(i) for i, _ in ov.kernel_map(c4, c4, 3, 1))
+    per_voxel = pairs / len(q) - 1  # without the centre
+    assert 4.0 < per_voxel < 13.0, per_voxel

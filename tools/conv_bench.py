@@ -52,6 +52,9 @@ def main():
     ap.add_argument("--gather", default="0,2")
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
     ap.add_argument("--sorted", default="0,1", help="gather-plan row order: 0 natural, 1 mask-sorted")
+    ap.add_argument("--points", type=int, default=0,
+                    help="micro-bench sweep (BASELINE configs[3]): use ONE random-plane cloud of this many points "
+                         "(10k .. 2M) instead of the batch of synthetic scans")
     args = ap.parse_args()
 
     from lidog_b200 import cabi
@@ -60,7 +63,7 @@ def main():
     from lidog_b200.lidog import synth
 
     dev = torch.device("cuda", 0)
-    scans = synth.make_batch(args.batch, 1234, args.shape, 7)
+    scans = [synth.make_plane_cloud(args.points, 1234)] if args.points else synth.make_batch(args.batch, 1234, args.shape, 7)
     pts = [torch.from_numpy(p).to(dev) for p, _ in scans]
     lab = [torch.from_numpy(l).to(dev) for _, l in scans]
     q = ME.utils.sparse_quantize_batch(pts, lab, 0.05, -1)
