@@ -15,3 +15,8 @@ for cfg in "LIDOG_G2_MMA2=0" "LIDOG_G2_MMA2=1"; do
   env $cfg timeout 300 python tools/conv_bench.py --cases net --gather 2 --sorted 1 --only fwd,dgrad --reps 10 2>&1 | tee -a gpurun_out/r2a_sweep_mma2.txt | cut -c1-120
 done
 LIDOG_G2_MMA2=1 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2a_bench_mma2.json 2> gpurun_out/r2a_bench_mma2.err; tail -1 gpurun_out/r2a_bench_mma2.err | cut -c1-200
+# 4. BASELINE configs[3]: micro-benchmark sweep over the point count on random-plane clouds (fwd / dgrad / wgrad)
+for n in 10000 100000 1000000 2000000; do
+  echo "== points $n" | tee -a gpurun_out/r2a_microbench.txt
+  timeout 300 python tools/conv_bench.py --points $n --cases all --gather 2 --sorted 1 --reps 10 2>&1 | tee -a gpurun_out/r2a_microbench.txt | cut -c1-120
+done
