@@ -95,3 +95,20 @@ class LidogTrainer:
         total.backward()
         self.optimizer.step()
         return total.detach()
+
+    def training_step_multi(self, sources):
+        """Multi-source step (PLTTrainer2DMulti.training_step, utils/pipelines/trainer_lighting_2d_multi.py:135-199):
+        one forward pass per source domain through the SAME model, each on its own batch / coordinate manager,
+        total = sum_i source_weights[i] * (loss_3d_i + loss_bev_i), one backward, one optimizer step.
+        `sources` = [(points_list, labels_list), ...] (two in the reference)."""
+        assert len(sources) == len(self.source_weights), "one weight per source domain"
+        batches = [self.voxelize(p, l) + (len(p),) for p, l in sources]
+        self.optimizer.zero_grad(set_to_none=True)
+        total = None
+        for w, (coords, feats, sem_labels, bev_labels, cm, n) in zip(self.source_weights, batches):
+            _, l3, l2 = self.forward_loss(coords, feats, sem_labels, bev_labels, n, cm)
+            term = w * (l3 + l2)
+            total = term if total is None else total + term
+        total.backward()
+        self.optimizer.step()
+        return total.detach()
