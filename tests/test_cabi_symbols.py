@@ -42,6 +42,10 @@ def test_host_only_entry_points(libpath):
     # argument validation happens before any CUDA call
     assert L.lg_quantize_points(None, None, -1, 0.05, 0.05, 0.05, None, None) == -1
     assert b"lg_quantize_points" in L.lg_last_error_string()
+    assert L.lg_quantize_points_f64(None, None, 0, 0.05, 0.05, 0.05, None, None) == 0   # empty cloud: nothing to do
+    assert L.lg_quantize_points_f64(None, None, 5, 0.05, 0.0, 0.05, None, None) == -1   # doubles arrive as doubles
+    assert L.lg_quantize_points_f64(None, None, 5, 0.05, 0.05, 0.05, None, None) == -1  # null pointers
+    assert b"lg_quantize_points_f64: null pointer" in L.lg_last_error_string()
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions(libpath):
