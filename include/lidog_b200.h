@@ -86,6 +86,26 @@ int lg_coords_unique(const int32_t* coords4, int64_t n, int32_t stride, void* ta
                      int32_t ignore_label, int32_t* colabels, int64_t* count_status, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Every coordinate level of a batch in ONE call: level 0 = lg_coords_unique(coords4, strides[0]) (labels / colabels
+ * apply to it), level l = lg_coords_unique(level l-1 coordinates, strides[l]).  The row count of a level reaches the
+ * next one on the DEVICE, so the host does not wait between levels: the caller sizes every level's arrays and table
+ * for the upper bound n (capacity >= lg_hash_capacity(n)), and reads all counts with one synchronisation -- the
+ * coordinate manager of ME.SparseTensor (utils/pipelines/trainer_lighting_2d.py:151) plus the four stride-2 maps of
+ * MinkUNet34 (utils/models/minkunet_bev.py:62,69,76,83) used to cost five host round trips per training step.
+ *   levels[l].inverse_map: row of level l for every row of the level below (level 0: for every input row);
+ *   counts_dev int64[2 * n_levels] = {n_unique, status} per level; counts_host (nullable, pinned host memory)
+ *   receives a copy on the stream.  Scratch: library arena. */
+typedef struct lgLevelOut {
+  void* table;
+  int64_t capacity;
+  int32_t* coords4;
+  int64_t* unique_map;
+  int64_t* inverse_map;
+} lgLevelOut;
+int lg_coords_pyramid(const int32_t* coords4, int64_t n, const int32_t* labels, int32_t ignore_label, int32_t* colabels,
+                      int32_t n_levels, const int32_t* strides /* host */, const lgLevelOut* levels /* host */,
+                      int64_t* counts_dev, int64_t* counts_host, void* stream);
+
 /* ------------------------------------------------------------------ kernel maps */
 
 /* Gather plan consumed by the convolution kernels.  For slot s of tile t = s / LG_TILE_ROWS and
@@ -167,9 +187,10 @@ int lg_prep_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout, void* 
  * utils/models/minkunet_bev.py:57-123):  Y[out_row[s], :] = out_scale * sum_k A16[nbr[k][s], :] @ B16[wk]^T
  * A16 [n_in][Ck] and B16 [K][N][Ck] are 16-bit (fmt), Ck % 32 == 0, N % 16 == 0, N <= 512.
  * out_scale: nullable device float (undoes lg_absmax_scale).  bias nullable [N].
- * gather_mode: 2 = super-tile pipeline (cp.async row gathers arriving on mbarriers, weight panels by TMA,
- *              up to 8 row tiles accumulating in TMEM per weight load; default, csrc/conv_tc2.cu);
- *              1 = first-generation kernel with TMA tile::gather4 rows; 0 = first generation, cp.async. */
+ * gather_mode: must be 2 = super-tile pipeline (cp.async row gathers arriving on mbarriers, weight panels by TMA,
+ *              up to 4 row tiles accumulating in TMEM per weight load; csrc/conv_tc2.cu).  The first-generation
+ *              kernels (0 = cp.async, 1 = TMA tile::gather4, measured 2.7x slower) left the library; their source
+ *              is kept in tools/legacy/conv_tc_gen1.cu as the record. */
 int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t Ck, const void* B16, int32_t N, int32_t flip_k,
                     int32_t fmt, const float* out_scale, const float* bias, float* Y, int32_t gather_mode,
                     void* stream);
@@ -179,6 +200,32 @@ size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin, int32_t C
 int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const void* dY16, int32_t Cout,
                      int32_t fmt, const float* out_scale, float* dW, int32_t gather_mode, void* workspace,
                      size_t workspace_bytes, void* stream);
+
+/* ---- layer-level entry points: ONE host call per MinkowskiConvolution each way (same contract as lg_conv_gemm_tc /
+ * lg_conv_wgrad_tc; utils/models/minkunet_bev.py:57-123).
+ * Forward: optionally (prep != 0) refreshes the 16-bit weight copies w16 [K][Cin][Cout] / w16t [K][Cout][Cin] from the
+ * fp32 parameter W -- the caller keeps them until the parameter changes -- then runs the gather-GEMM.
+ * stat_partials (nullable, float [4 * n_slots / 128][2 * Cout]): per-(tile, epilogue warp) column sums and sums of
+ * squares of Y, written by the GEMM epilogue for the batch norm that follows (lgBnBranch.stat_partials), so the
+ * statistics pass over Y is never run.  Needs Cout a multiple of 32 per column block. */
+int lg_conv_layer_forward(const lgConvPlan* plan, const void* X16, int32_t Cin, const float* W, int32_t Cout, void* w16,
+                          void* w16t, int32_t prep, int32_t fmt, const float* bias, float* Y, float* stat_partials,
+                          void* stream);
+/* Backward: dX = inv_scale * dgrad (skipped when dX is NULL), dW = inv_scale * wgrad (skipped when dW is NULL);
+ * dY16 is the 16-bit gradient scaled by 1 / inv_scale[0] (inv_scale nullable).  Split-K partials: library arena. */
+int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConvPlan* plan_wgrad, int32_t flip_dgrad,
+                           const void* X16, int32_t Cin, const void* dY16, int32_t Cout, const void* w16, int32_t fmt,
+                           const float* inv_scale, float* dX, float* dW, void* stream);
+
+/* Library-owned scratch arena (one block per device and stream, outside any caching allocator): bytes currently held,
+ * and release (synchronises).  The layer-level calls size it themselves. */
+size_t lg_arena_bytes(void);
+int lg_arena_release(void);
+
+/* Diagnostics of the tensor-core pipeline (tools/prof_roles.py, tools/trace_units.py; active with LIDOG_DBG & 8):
+ * per-role wait cycles of CTA 0 (16 counters) and the per-unit event trace [5][512]. */
+int lg_debug_profile(long long* out16, int reset);
+int lg_debug_trace(long long* out);
 
 /* ------------------------------------------------------------------ fused batch norm (+ ReLU, residual, operand cast)
  *
@@ -219,6 +266,47 @@ int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, const float
                     const float* x2, const float* stats2, const float* coef2, int32_t relu, int64_t n, int32_t C,
                     float* dx, void* dx16, const float* scale, float* dx2, void* dx2_16, const float* scale2,
                     float* dres, void* dres16, const float* scale_r, int32_t fmt, void* stream);
+
+/* ---- layer-level entry points: ONE host call per MinkowskiBatchNorm(+ReLU, +residual) each way.
+ *
+ * The host path of a training step was as long as its GPU time (round 1: 44 ms of Python for a 45 ms step), so the
+ * reference-facing layer (lidog_b200/me/norm.py) makes one call per fused layer instead of 5-9.  Scratch comes from the
+ * library's own arena (lg_arena_bytes), nothing is allocated per call; the SyncBN exchange (train_lidog.py:228) runs
+ * INSIDE the tail kernel of the statistics pass over NVLink peer memory when `peer` is given (see lg_peer_sum for the
+ * protocol; the call consumes 1 epoch per branch forward, 1 epoch backward).
+ *   stats float[4C + 2]: [mean, invstd, scale, shift] x C, then the row count over all ranks as one double. */
+typedef struct lgPeerCtx {
+  void* const* bufs; /* HOST array: device address in this process of every rank's exchange buffer */
+  int32_t world, rank;
+  uint64_t epoch; /* first epoch this call may use (1, 2, ...; identical sequence on every rank) */
+} lgPeerCtx;
+typedef struct lgBnBranch {
+  const float* x;             /* [n, C] input of this BN */
+  const float* stat_partials; /* nullable: [n_stat_rows, 2C] per-tile (sum, sum of squares) rows written by the */
+  int64_t n_stat_rows;        /*   epilogue of the convolution that produced x (lg_conv_layer_forward) */
+  const float *gamma, *beta;  /* nullable */
+  float *running_mean, *running_var; /* nullable; updated as torch does (momentum, unbiased variance) */
+  int64_t* num_batches_tracked;      /* nullable */
+  float eps, momentum;
+  float* stats; /* out [4C + 2], kept by the caller for the backward */
+} lgBnBranch;
+/* y = act(BN_a(x_a) [+ BN_b(x_b)] [+ res]); y16 (nullable) = the 16-bit operand copy of y. */
+int lg_bn_layer_forward(const lgBnBranch* a, const lgBnBranch* b /* nullable */, const float* res /* nullable */,
+                        int32_t relu, int64_t n, int32_t C, float* y, void* y16, int32_t fmt,
+                        const lgPeerCtx* peer /* nullable */, void* stream);
+typedef struct lgBnBwdBranch {
+  const float* x;
+  const float* stats; /* [4C + 2] from the forward */
+  const float* gamma; /* nullable */
+  float* dx;          /* out [n, C] */
+  void* dx16;         /* nullable out: dx * scale in the 16-bit format, for the convolution backward */
+  float *dgamma, *dbeta; /* nullable out [C] (this rank's sums: DDP reduces parameter gradients) */
+} lgBnBwdBranch;
+/* Backward of the above.  scales float[12]: [4i .. 4i+2] = {2^k, 2^-k, bound} of branch i's dx16. dres (nullable)
+ * receives g = dy * [y > 0], the gradient of the plain residual. */
+int lg_bn_layer_backward(const float* dy, const float* y, int32_t relu, int64_t n, int32_t C, const lgBnBwdBranch* a,
+                         const lgBnBwdBranch* b /* nullable */, float* dres, int32_t fmt, float* scales,
+                         const lgPeerCtx* peer /* nullable */, void* stream);
 
 /* ------------------------------------------------------------------ SyncBN exchange over peer memory
  *

@@ -30,6 +30,27 @@ class ConvPlan(C.Structure):
 
 _PP = C.POINTER(ConvPlan)
 
+
+class PeerCtx(C.Structure):
+    _fields_ = [("bufs", C.POINTER(C.c_void_p)), ("world", _i32), ("rank", _i32), ("epoch", C.c_uint64)]
+
+
+class BnBranch(C.Structure):
+    _fields_ = [("x", _vp), ("stat_partials", _vp), ("n_stat_rows", _i64), ("gamma", _vp), ("beta", _vp),
+                ("running_mean", _vp), ("running_var", _vp), ("num_batches_tracked", _vp), ("eps", _f32),
+                ("momentum", _f32), ("stats", _vp)]
+
+
+class BnBwdBranch(C.Structure):
+    _fields_ = [("x", _vp), ("stats", _vp), ("gamma", _vp), ("dx", _vp), ("dx16", _vp), ("dgamma", _vp), ("dbeta", _vp)]
+
+
+class LevelOut(C.Structure):
+    _fields_ = [("table", _vp), ("capacity", _i64), ("coords4", _vp), ("unique_map", _vp), ("inverse_map", _vp)]
+
+
+_PB, _PBB, _PPC = C.POINTER(BnBranch), C.POINTER(BnBwdBranch), C.POINTER(PeerCtx)
+
 SIGNATURES = {
     "lg_version": (C.c_int, []),
     "lg_last_error_string": (C.c_char_p, []),
@@ -40,6 +61,7 @@ SIGNATURES = {
     "lg_quantize_points_f64": (C.c_int, [_vp, _vp, _i64, C.c_double, C.c_double, C.c_double, _vp, _vp]),
     "lg_coords_unique_workspace": (_sz, [_i64]),
     "lg_coords_unique": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "lg_coords_pyramid": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, C.POINTER(_i32), C.POINTER(LevelOut), _vp, _vp, _vp]),
     "lg_kernel_map": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "lg_kernel_map_sorted_workspace": (_sz, [_i64, _i32]),
     "lg_kernel_map_sorted": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -55,6 +77,14 @@ SIGNATURES = {
     "lg_conv_gemm_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "lg_conv_wgrad_tc_workspace": (_sz, [_PP, _i32, _i32]),
     "lg_conv_wgrad_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "lg_conv_layer_forward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "lg_conv_layer_backward": (C.c_int, [_PP, _PP, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "lg_arena_bytes": (_sz, []),
+    "lg_arena_release": (C.c_int, []),
+    "lg_debug_profile": (C.c_int, [_vp, C.c_int]),
+    "lg_debug_trace": (C.c_int, [_vp]),
+    "lg_bn_layer_forward": (C.c_int, [_PB, _PB, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _PPC, _vp]),
+    "lg_bn_layer_backward": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _PBB, _PBB, _vp, _i32, _vp, _PPC, _vp]),
     "lg_bn_workspace": (_sz, [_i64, _i32]),
     "lg_bn_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lg_bn_finalize": (C.c_int, [_vp, C.c_double, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
@@ -74,8 +104,9 @@ SIGNATURES = {
 }
 
 
-# CUDA kernels launched by one call of each entry point (memsets not counted); bench.py multiplies
-# these by the call counts to report `gpu_launches`.
+# CUDA kernels launched by one call of each entry point (memsets not counted; variable ones are counted by the
+# caller through `count_launches`).  bench.py runs one CENSUS step with counting on to report `gpu_launches`; the
+# timed steps go straight to the CDLL.
 KERNELS_PER_CALL = {
     "lg_quantize_points": 1, "lg_quantize_points_f64": 1, "lg_coords_unique": 7, "lg_kernel_map": 1, "lg_kernel_map_sorted": 7, "lg_kernel_map_pairs": 3,
     "lg_kernel_map_up2": 9, "lg_conv_gemm_simt": 1, "lg_conv_wgrad_simt": 2, "lg_cast_rows": 1,
@@ -83,12 +114,14 @@ KERNELS_PER_CALL = {
     "lg_bev_forward": 2, "lg_bev_backward": 3,
     "lg_bn_stats": 2, "lg_bn_finalize": 1, "lg_bn_apply": 1, "lg_bn_bwd_stats": 2, "lg_bn_bwd_finalize": 1,
     "lg_bn_bwd_gscale": 1, "lg_bn_bwd_apply": 1, "lg_peer_sum": 1,
+    "lg_bn_layer_backward": 3,
 }
 COUNTS: dict = {}
+_RAW = None
 
 
 class _Counting:
-    """Thin proxy over the CDLL that counts calls per entry point."""
+    """Proxy over the CDLL that counts calls per entry point (census passes only)."""
 
     def __init__(self, cdll):
         self._cdll = cdll
@@ -108,13 +141,32 @@ class _Counting:
         return fn
 
 
+def counting(on: bool) -> None:
+    """Census mode: count library calls (and the launches callers report through `count_launches`)."""
+    global _LIB
+    lib()
+    _LIB = _Counting(_RAW) if on else _RAW
+    if on:
+        COUNTS.clear()
+
+
+def is_counting() -> bool:
+    return _LIB is not None and _LIB is not _RAW
+
+
+def count_launches(name: str, n: int) -> None:
+    """Launch count of a call whose kernel count depends on its arguments (the fused layer entry points)."""
+    if _LIB is not _RAW:
+        COUNTS["#" + name] = COUNTS.get("#" + name, 0) + n
+
+
 def kernel_launches() -> int:
-    return sum(KERNELS_PER_CALL[k] * v for k, v in COUNTS.items())
+    return sum(v if k.startswith("#") else KERNELS_PER_CALL[k] * v for k, v in COUNTS.items())
 
 
 def lib():
     """Load the shared library once; fail loudly when it is not there."""
-    global _LIB
+    global _LIB, _RAW
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} not built: run `python -m lidog_b200.build` (no CPU fallback exists)")
@@ -122,7 +174,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        _LIB = _Counting(L)
+        _RAW = _LIB = L
     return _LIB
 
 
@@ -133,6 +185,11 @@ def check(rc: int, what: str = ""):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    """Raw handle of torch's current stream on the device of tensor `t` (not the thread's current device)."""
+    return torch._C._cuda_getCurrentRawStream(t.device.index)
 
 
 def stream():
@@ -149,6 +206,15 @@ def device_info():
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     check(lib().lg_device_info(C.byref(a), C.byref(b), C.byref(c)), "lg_device_info")
     return a.value, b.value, c.value
+
+
+def peer_ctx(ex, n_epochs: int):
+    """lgPeerCtx of a me.peer.PeerExchange for a call that consumes `n_epochs` exchanges (None -> NULL)."""
+    if ex is None:
+        return None
+    ctx = PeerCtx(ex.ptrs, ex.world, ex.rank, ex.epoch + 1)
+    ex.epoch += n_epochs
+    return C.byref(ctx)
 
 
 def make_plan(nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in) -> ConvPlan:

@@ -18,8 +18,11 @@
 // Bound: HBM.  Algorithmic bytes per element: forward 4 (stats) + 4+4+2 (apply), backward 12 + 12+4+2.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "peer.cuh"
+#include "runtime.cuh"
 
 namespace lg {
 
@@ -378,6 +381,222 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ------------------------------------------------------------------------------------ fused layer tails
+// One kernel between the statistics pass and the apply pass of a layer: second-stage reduction of the block
+// partials (fixed order), the SyncBN exchange over NVLink peer memory (the protocol of peer.cu, inline: the LAST
+// block of the grid publishes the sums, raises the epoch flag, waits for the peers' flags and adds their vectors in
+// rank order), and the per-channel finalisation.  It replaces k_bn_reduce + k_peer_sum + k_bn_finalize (forward) and
+// k_bn_bwd_reduce + k_peer_sum + 2 x k_bn_bwd_finalize + k_bn_gscale (backward): 62 x 3 + 55 x 5 launches per step.
+struct PeerCtx {
+  PeerSlot* buf[kPeerMaxWorld];
+  int world, rank;
+  unsigned long long epoch;
+};
+
+// grid (ceil(width / 128), S), block (128, 8): block (bx, by) folds the partial rows of slice by for 128 columns
+// into slice_out[by][c] (double).  Returns true in the block that finished last (its threads then see every slice).
+__device__ __forceinline__ bool tail_reduce(const float* __restrict__ partial, int n_partials, int width, int n_sum,
+                                            double* __restrict__ slice_out, int* ticket) {
+  __shared__ double sm[kRedY][kRedX];
+  __shared__ int s_last;
+  const int c = blockIdx.x * kRedX + threadIdx.x;
+  const int S = gridDim.y;
+  const int per = (n_partials + S - 1) / S;
+  const int p0 = blockIdx.y * per, p1 = min(n_partials, p0 + per);
+  const bool is_sum = c < n_sum;  // columns >= n_sum are maxima
+  double a = 0.0;
+  if (c < width)
+    for (int p = p0 + threadIdx.y; p < p1; p += kRedY) {
+      const double v = (double)__ldg(partial + (size_t)p * width + c);
+      a = is_sum ? a + v : fmax(a, v);
+    }
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < width) {
+    for (int y = 1; y < kRedY; ++y) a = is_sum ? a + sm[y][threadIdx.x] : fmax(a, sm[y][threadIdx.x]);
+    slice_out[(size_t)blockIdx.y * width + c] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int t = atomicAdd(ticket, 1);
+    s_last = (t == (int)(gridDim.x * gridDim.y) - 1);
+    if (s_last) *ticket = 0;  // the slot is zero again for the next launch that draws it
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// vec[0..n) (global, written by this block) -> sum over ranks in rank order, in place.  All 1024 threads call it.
+__device__ __forceinline__ void tail_exchange(double* vec, int n, const PeerCtx& pc, int* err) {
+  if (pc.world <= 1) return;
+  const int tid = threadIdx.y * kRedX + threadIdx.x, nt = kRedX * kRedY;
+  PeerSlot* mine = pc.buf[pc.rank] + (pc.epoch % kPeerSlots);
+  for (int i = tid; i < n; i += nt) mine->data[i] = vec[i];
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) st_release_sys(&mine->flag, pc.epoch);
+  if (tid < pc.world && tid != pc.rank) {
+    const unsigned long long* f = &(pc.buf[tid] + (pc.epoch % kPeerSlots))->flag;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(f) < pc.epoch) {
+      if (++spins > (1ull << 28)) {
+        if (err) atomicExch(err, 100 + tid);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    double a = 0.0;
+    for (int r = 0; r < pc.world; ++r) {
+      const PeerSlot* s = pc.buf[r] + (pc.epoch % kPeerSlots);
+      a += (r == pc.rank) ? vec[i] : ld_relaxed_sys_f64(&s->data[i]);
+    }
+    vec[i] = a;  // each thread rewrites only what it read itself; the peers read the published copy
+  }
+}
+
+struct BnFwdTail {
+  const float* partial;  // [n_partials][2C]
+  int n_partials, C;
+  double n_local;
+  double* slices;  // [S][2C] scratch
+  double* sums;    // [2C + 1] scratch
+  const float *gamma, *beta;
+  float eps, momentum;
+  float *running_mean, *running_var;
+  long long* nbt;
+  float* stats;  // [4C + 2]: mean, invstd, scale, shift, then the (global) row count as one double
+  int* ticket;
+  int* err;
+  PeerCtx peer;
+};
+
+__global__ void __launch_bounds__(kRedX* kRedY) k_bn_tail_fwd(const BnFwdTail t) {
+  const int C = t.C, W = 2 * C;
+  if (!tail_reduce(t.partial, t.n_partials, W, W, t.slices, t.ticket)) return;
+  const int tid = threadIdx.y * kRedX + threadIdx.x, nt = kRedX * kRedY, S = gridDim.y;
+  for (int c = tid; c < W; c += nt) {
+    double a = 0.0;
+    for (int s = 0; s < S; ++s) a += __ldcg(t.slices + (size_t)s * W + c);
+    t.sums[c] = a;
+  }
+  if (tid == 0) t.sums[W] = t.n_local;
+  __syncthreads();
+  tail_exchange(t.sums, W + 1, t.peer, t.err);
+  __syncthreads();
+  const double count = t.sums[W];
+  if (tid == 0) {
+    *reinterpret_cast<double*>(t.stats + 4 * C) = count;
+    if (t.nbt) *t.nbt += 1;
+  }
+  for (int c = tid; c < C; c += nt) {
+    const double mean = t.sums[c] / count;
+    double var = t.sums[C + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)t.eps));
+    const float gm = t.gamma ? t.gamma[c] : 1.f, bt = t.beta ? t.beta[c] : 0.f;
+    const float scale = gm * invstd;
+    t.stats[c] = (float)mean;
+    t.stats[C + c] = invstd;
+    t.stats[2 * C + c] = scale;
+    t.stats[3 * C + c] = bt - (float)mean * scale;
+    if (t.running_mean) t.running_mean[c] = (1.f - t.momentum) * t.running_mean[c] + t.momentum * (float)mean;
+    if (t.running_var) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      t.running_var[c] = (1.f - t.momentum) * t.running_var[c] + t.momentum * (float)unbiased;
+    }
+  }
+}
+
+struct BnBwdBranch {
+  const float* gamma;
+  const float* stats;  // [4C + 2] of the forward
+  float *coef, *dgamma, *dbeta, *scale;  // coef [3C] scratch; scale float[4]
+};
+struct BnBwdTail {
+  const float* partial;  // [n_partials][6C]: sums 3C | maxes 3C
+  int n_partials, C, n_branches, want_gscale;
+  double* slices;  // [S][6C]
+  double* sums;    // [6C]: local sums 3C | global sums 3C
+  float* maxes;    // [3C]
+  BnBwdBranch br[2];
+  float* scale_r;  // float[4] for the plain residual gradient g (want_gscale)
+  int* ticket;
+  int* err;
+  PeerCtx peer;
+};
+
+__device__ __forceinline__ float block_max_1024(float v, float* s_w) {
+  const int tid = threadIdx.y * kRedX + threadIdx.x;
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if ((tid & 31) == 0) s_w[tid >> 5] = v;
+  __syncthreads();
+  float m = 0.f;
+  for (int w = 0; w < 32; ++w) m = fmaxf(m, s_w[w]);
+  return m;
+}
+__device__ __forceinline__ void write_scale(float m, float* out) {
+  float s = 1.f;
+  if (m > 0.f && m <= 3.0e38f) {
+    int e;
+    frexpf(m, &e);
+    s = ldexpf(1.f, 12 - e);
+  }
+  out[0] = s, out[1] = 1.f / s, out[2] = m;
+}
+
+__global__ void __launch_bounds__(kRedX* kRedY) k_bn_tail_bwd(const BnBwdTail t) {
+  __shared__ float s_w[32];
+  const int C = t.C, W = 6 * C;
+  if (!tail_reduce(t.partial, t.n_partials, W, 3 * C, t.slices, t.ticket)) return;
+  const int tid = threadIdx.y * kRedX + threadIdx.x, nt = kRedX * kRedY, S = gridDim.y;
+  for (int c = tid; c < W; c += nt) {
+    const bool is_sum = c < 3 * C;
+    double a = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const double v = __ldcg(t.slices + (size_t)s * W + c);
+      a = is_sum ? a + v : fmax(a, v);
+    }
+    if (is_sum)
+      t.sums[c] = a, t.sums[3 * C + c] = a;
+    else
+      t.maxes[c - 3 * C] = (float)a;
+  }
+  __syncthreads();
+  tail_exchange(t.sums + 3 * C, 3 * C, t.peer, t.err);  // dx needs the sums over every rank; dgamma / dbeta stay local
+  __syncthreads();
+  for (int b = 0; b < t.n_branches; ++b) {
+    const BnBwdBranch& br = t.br[b];
+    const double count = *reinterpret_cast<const double*>(br.stats + 4 * C);
+    float bound = 0.f;
+    for (int c = tid; c < C; c += nt) {
+      const float invstd = br.stats[C + c], gm = br.gamma ? br.gamma[c] : 1.f;
+      const double sg = t.sums[3 * C + c], sgx = t.sums[3 * C + (1 + b) * C + c];
+      const float a = gm * invstd;
+      const float bb = (float)(-(double)gm * invstd * invstd * invstd * sgx / count);
+      const float c0 = (float)(-(double)gm * invstd * sg / count);
+      br.coef[c] = a, br.coef[C + c] = bb, br.coef[2 * C + c] = c0;
+      if (br.dgamma) br.dgamma[c] = (float)(t.sums[(1 + b) * C + c] * invstd);
+      if (br.dbeta) br.dbeta[c] = (float)t.sums[c];
+      bound = fmaxf(bound, fabsf(a) * t.maxes[c] + fabsf(bb) * t.maxes[(1 + b) * C + c] + fabsf(c0));
+    }
+    const float m = block_max_1024(bound, s_w);
+    if (tid == 0) write_scale(m, br.scale);
+  }
+  if (t.want_gscale) {
+    float m = 0.f;
+    for (int c = tid; c < C; c += nt) m = fmaxf(m, t.maxes[c]);
+    m = block_max_1024(m, s_w);
+    if (tid == 0) write_scale(m, t.scale_r);
+  }
+}
+
 static int bn_blocks(int64_t n) {
   int64_t b = n / 128;
   if (b < 1) b = 1;
@@ -494,6 +713,167 @@ extern "C" int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, 
   k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256 * kBwdU), 256, 0, (cudaStream_t)stream_>>>(
       dy, y, x, stats, coef, x2, stats2, coef2, relu, n4, C, dx, (unsigned short*)dx16, scale, dx2,
       (unsigned short*)dx2_16, scale2, dres, (unsigned short*)dres16, scale_r, fmt);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused layer entry points
+namespace lg {
+
+static int peer_ctx(const lgPeerCtx* p, PeerCtx* out, int extra_epoch, const char* who) {
+  memset(out, 0, sizeof(*out));
+  out->world = 1;
+  if (!p || p->world <= 1) return LG_OK;
+  LG_CHECK_ARG(p->bufs && p->world <= kPeerMaxWorld && p->rank >= 0 && p->rank < p->world && p->epoch >= 1,
+               "%s: bad peer exchange context", who);
+  for (int r = 0; r < p->world; ++r) out->buf[r] = (PeerSlot*)p->bufs[r];
+  out->world = p->world;
+  out->rank = p->rank;
+  out->epoch = p->epoch + (unsigned long long)extra_epoch;
+  return LG_OK;
+}
+
+static int tail_slices(int64_t n_partials) {
+  int64_t s = (n_partials + 63) / 64;
+  return (int)(s < 1 ? 1 : (s > 32 ? 32 : s));
+}
+
+static size_t fwd_scratch(int64_t n, int C, int64_t n_stat_rows) {
+  size_t b = 0;
+  if (!n_stat_rows) b += arena_pad(sizeof(float) * (size_t)kBnMaxBlocks * 2 * C);
+  b += arena_pad(sizeof(double) * 32 * 2 * C) + arena_pad(sizeof(double) * (2 * C + 1));
+  return b;
+}
+
+// statistics of one branch: block partials (or the partials a convolution epilogue already wrote) -> tail kernel
+static int bn_branch_forward(const lgBnBranch* b, int64_t n, int C, ArenaCursor* ar, const lgPeerCtx* peer, int peer_k,
+                             int* err, cudaStream_t stream) {
+  const float* partial = b->stat_partials;
+  int64_t n_partials = b->n_stat_rows;
+  if (!partial) {
+    const int nb = bn_blocks(n);
+    float* p = (float*)arena_take(ar, sizeof(float) * (size_t)kBnMaxBlocks * 2 * C);
+    k_bn_stats<<<nb, kBnThreads, red_smem(C), stream>>>(b->x, n, C, p);
+    LG_LAUNCH_OK();
+    partial = p;
+    n_partials = nb;
+  }
+  BnFwdTail t;
+  t.partial = partial;
+  t.n_partials = (int)n_partials;
+  t.C = C;
+  t.n_local = (double)n;
+  const int S = tail_slices(n_partials);
+  t.slices = (double*)arena_take(ar, sizeof(double) * 32 * 2 * C);
+  t.sums = (double*)arena_take(ar, sizeof(double) * (2 * C + 1));
+  t.gamma = b->gamma, t.beta = b->beta, t.eps = b->eps, t.momentum = b->momentum;
+  t.running_mean = b->running_mean, t.running_var = b->running_var, t.nbt = (long long*)b->num_batches_tracked;
+  t.stats = b->stats;
+  t.err = err;
+  int rc = counter_slot(&t.ticket);
+  if (rc) return rc;
+  rc = peer_ctx(peer, &t.peer, peer_k, "lg_bn_layer_forward");
+  if (rc) return rc;
+  k_bn_tail_fwd<<<dim3((unsigned)ceil_div(2 * C, kRedX), (unsigned)S), dim3(kRedX, kRedY), 0, stream>>>(t);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+
+}  // namespace lg
+
+extern "C" int lg_bn_layer_forward(const lgBnBranch* a, const lgBnBranch* b, const float* res, int32_t relu, int64_t n,
+                                   int32_t C, float* y, void* y16, int32_t fmt, const lgPeerCtx* peer, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // n = 0 is legal: under SyncBN a rank without voxels at this stride still takes part in the exchange
+  int rc = bn_check(n > 0 ? n : 1, C, "lg_bn_layer_forward");
+  if (rc) return rc;
+  LG_CHECK_ARG(n >= 0 && a && a->stats && (!b || b->stats) && (n == 0 || (a->x && y && (!b || b->x))),
+               "lg_bn_layer_forward: null pointer");
+  LG_CHECK_ARG(n < ((int64_t)1 << 31) * 32, "lg_bn_layer_forward: too many rows");
+  int sm = 0;
+  int* err = nullptr;
+  rc = tc_runtime(&sm, &err);
+  if (rc) return rc;
+  ArenaCursor ar;
+  rc = arena_begin(stream, fwd_scratch(n, C, a->stat_partials ? a->n_stat_rows : 0) +
+                               (b ? fwd_scratch(n, C, b->stat_partials ? b->n_stat_rows : 0) : 0),
+                   &ar);
+  if (rc) return rc;
+  rc = bn_branch_forward(a, n, C, &ar, peer, 0, err, stream);
+  if (rc) return rc;
+  if (b) {
+    rc = bn_branch_forward(b, n, C, &ar, peer, 1, err, stream);
+    if (rc) return rc;
+  }
+  const int64_t n4 = n * (C >> 2);
+  if (n4 > 0) {
+    k_bn_apply<<<(unsigned)ceil_div(n4, 256 * kApplyU), 256, 0, stream>>>(a->x, a->stats, b ? b->x : nullptr,
+                                                                          b ? b->stats : nullptr, res, relu, n4, C, y,
+                                                                          (unsigned short*)y16, fmt);
+    LG_LAUNCH_OK();
+  }
+  return LG_OK;
+}
+
+extern "C" int lg_bn_layer_backward(const float* dy, const float* y, int32_t relu, int64_t n, int32_t C,
+                                    const lgBnBwdBranch* a, const lgBnBwdBranch* b, float* dres, int32_t fmt,
+                                    float* scales /* [12]: a, b, residual */, const lgPeerCtx* peer, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = bn_check(n > 0 ? n : 1, C, "lg_bn_layer_backward");
+  if (rc) return rc;
+  LG_CHECK_ARG(n >= 0 && a && a->stats && scales && (!b || b->stats) &&
+                   (n == 0 || (dy && a->x && a->dx && (!relu || y) && (!b || (b->x && b->dx)))),
+               "lg_bn_layer_backward: null pointer");
+  int sm = 0;
+  int* err = nullptr;
+  rc = tc_runtime(&sm, &err);
+  if (rc) return rc;
+  ArenaCursor ar;
+  rc = arena_begin(stream,
+                   arena_pad(sizeof(float) * (size_t)kBnMaxBlocks * 6 * C) + arena_pad(sizeof(double) * 32 * 6 * C) +
+                       arena_pad(sizeof(double) * 6 * C) + arena_pad(sizeof(float) * 3 * C) +
+                       2 * arena_pad(sizeof(float) * 3 * C),
+                   &ar);
+  if (rc) return rc;
+  const int nb = bn_blocks(n);
+  float* partial = (float*)arena_take(&ar, sizeof(float) * (size_t)kBnMaxBlocks * 6 * C);
+  k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
+                                                          b ? b->stats : nullptr, relu, n, C, partial);
+  LG_LAUNCH_OK();
+  BnBwdTail t;
+  memset(&t, 0, sizeof(t));
+  t.partial = partial;
+  t.n_partials = nb;
+  t.C = C;
+  t.n_branches = b ? 2 : 1;
+  t.want_gscale = 0;  // the residual gradient feeds an elementwise backward, never a 16-bit convolution operand
+  t.slices = (double*)arena_take(&ar, sizeof(double) * 32 * 6 * C);
+  t.sums = (double*)arena_take(&ar, sizeof(double) * 6 * C);
+  t.maxes = (float*)arena_take(&ar, sizeof(float) * 3 * C);
+  const lgBnBwdBranch* brs[2] = {a, b};
+  for (int i = 0; i < t.n_branches; ++i) {
+    t.br[i].gamma = brs[i]->gamma;
+    t.br[i].stats = brs[i]->stats;
+    t.br[i].coef = (float*)arena_take(&ar, sizeof(float) * 3 * C);
+    t.br[i].dgamma = brs[i]->dgamma;
+    t.br[i].dbeta = brs[i]->dbeta;
+    t.br[i].scale = scales + 4 * i;
+  }
+  t.scale_r = scales + 8;
+  t.err = err;
+  rc = counter_slot(&t.ticket);
+  if (rc) return rc;
+  rc = peer_ctx(peer, &t.peer, 0, "lg_bn_layer_backward");
+  if (rc) return rc;
+  k_bn_tail_bwd<<<dim3((unsigned)ceil_div(6 * C, kRedX), (unsigned)tail_slices(nb)), dim3(kRedX, kRedY), 0, stream>>>(t);
+  LG_LAUNCH_OK();
+  const int64_t n4 = n * (C >> 2);
+  const bool use16 = a->dx16 != nullptr;
+  if (n4 > 0)
+    k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256 * kBwdU), 256, 0, stream>>>(
+      dy, y, a->x, a->stats, t.br[0].coef, b ? b->x : nullptr, b ? b->stats : nullptr, b ? t.br[1].coef : nullptr, relu,
+      n4, C, a->dx, (unsigned short*)a->dx16, use16 ? scales : nullptr, b ? b->dx : nullptr,
+      b ? (unsigned short*)b->dx16 : nullptr, (b && b->dx16) ? scales + 4 : nullptr, dres, nullptr, nullptr, fmt);
   LG_LAUNCH_OK();
   return LG_OK;
 }

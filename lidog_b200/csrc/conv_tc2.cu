@@ -21,14 +21,13 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "runtime.cuh"
 #include "tc_ptx.cuh"
 
 namespace lg {
 
 int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
                            cudaStream_t stream);
-int tc_make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows);
-int tc_runtime(int* sm_count, int** err_word);
 
 namespace v2 {
 using namespace ptx;
@@ -206,6 +205,7 @@ struct Gemm2Args {
   lgConvPlan plan;
   const uint16_t* A;  // [n_in][Ck]
   float* Y;           // [n_out][N]
+  float* stats;       // nullable: [n_tiles * 4][2N] per-(tile, epilogue warp) column sums / sums of squares of Y
   const float* out_scale;
   const float* bias;
   int Ck, N, n_blk, flip, umma_fmt;
@@ -619,6 +619,10 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
           int64_t row = g.plan.out_row ? (int64_t)g.plan.out_row[s] : s;
           const bool row_ok = row >= 0 && row < g.plan.n_out;
           float* yrow = g.Y + (row_ok ? row : 0) * g.N + n0;
+          // BN statistics of the layer that follows: this warp's 32 rows contribute one partial
+          // row [sum | sum of squares] per tile; a fixed shuffle order and a fixed (tile, warp) slot keep the later
+          // reduction deterministic although tiles are handed out dynamically.
+          float* strow = g.stats ? g.stats + ((tile0 + t) * kEpiWarps + warp) * 2 * (int64_t)g.N + n0 : nullptr;
           if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
             if (row_ok)
               for (int n = 0; n < g.n_blk; n += 4) {
@@ -626,6 +630,17 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
                 if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
                 *reinterpret_cast<float4*>(yrow + n) = o;
               }
+            if (strow) {
+              const int valid = __popc(__ballot_sync(0xffffffffu, row_ok));
+              for (int n = 4 * lane; n < g.n_blk; n += 128) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) b4 = *reinterpret_cast<const float4*>(g.bias + n0 + n);
+                const float v = (float)valid;
+                *reinterpret_cast<float4*>(strow + n) = make_float4(v * b4.x, v * b4.y, v * b4.z, v * b4.w);
+                *reinterpret_cast<float4*>(strow + g.N + n) =
+                    make_float4(v * b4.x * b4.x, v * b4.y * b4.y, v * b4.z * b4.z, v * b4.w * b4.w);
+              }
+            }
           } else {
             // TMEM lane = tile row, so a thread holds 32 consecutive columns of ONE row; storing them directly
             // makes every warp store touch 32 different lines (measured: the epilogue was store-bound).  The
@@ -655,11 +670,30 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
                 *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * q) = o;
               }
               __syncwarp();
+              float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = cs;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
-                if (srow[j] >= 0 && !(dbg & 32))  // dbg 32: experiment without the result stores
-                  *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
+                if (srow[j] >= 0) {
+                  if (!(dbg & 32))  // dbg 32: experiment without the result stores
+                    *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
+                  cs.x += o.x, cs.y += o.y, cs.z += o.z, cs.w += o.w;
+                  cq.x = fmaf(o.x, o.x, cq.x), cq.y = fmaf(o.y, o.y, cq.y), cq.z = fmaf(o.z, o.z, cq.z),
+                  cq.w = fmaf(o.w, o.w, cq.w);
+                }
+              }
+              if (strow) {  // lanes l, l+8, l+16, l+24 hold the same 4 columns of different rows
+#pragma unroll
+                for (int d = 8; d <= 16; d <<= 1) {
+                  cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d), cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
+                  cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d), cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+                  cq.x += __shfl_xor_sync(0xffffffffu, cq.x, d), cq.y += __shfl_xor_sync(0xffffffffu, cq.y, d);
+                  cq.z += __shfl_xor_sync(0xffffffffu, cq.z, d), cq.w += __shfl_xor_sync(0xffffffffu, cq.w, d);
+                }
+                if (lane < 8) {
+                  *reinterpret_cast<float4*>(strow + n + 4 * lane) = cs;
+                  *reinterpret_cast<float4*>(strow + g.N + n + 4 * lane) = cq;
+                }
               }
               __syncwarp();
             }
@@ -987,19 +1021,6 @@ static inline size_t tail_bytes(int sa, int sb, int ni = 8 * kProdWarps) {  // +
 
 }  // namespace v2
 
-// Schedule counters: 64 slots of 8 ints, handed out round-robin so launches in flight on different
-// streams never share one; every kernel leaves its slot zeroed.
-static int* g_sched_pool = nullptr;
-static unsigned g_sched_seq = 0;
-static int sched_slot(int** out) {
-  if (!g_sched_pool) {
-    LG_CUDA_OK(cudaMalloc(&g_sched_pool, 64 * 8 * sizeof(int)));
-    LG_CUDA_OK(cudaMemset(g_sched_pool, 0, 64 * 8 * sizeof(int)));
-  }
-  *out = g_sched_pool + 8 * (g_sched_seq++ % 64);
-  return LG_OK;
-}
-
 int debug_profile(long long* out16, int reset) {
   if (out16) LG_CUDA_OK(cudaMemcpyFromSymbol(out16, v2::g_prof, sizeof(long long) * 16));
   if (reset) {
@@ -1009,10 +1030,30 @@ int debug_profile(long long* out16, int reset) {
   return LG_OK;
 }
 
+// Experiment switches, read ONCE per process (they used to cost ~10 getenv calls per launch):
+//   LIDOG_DBG        instrumented instantiation + experiment bits (see Gemm2Args::dbg)
+//   LIDOG_ACC_SETS   1 = single accumulator set
+//   LIDOG_G2_OPT     bit 2 = deep weight-panel ring, bit 4 = L2 row prefetch (measured slower, off)
+//   LIDOG_G2_SB / LIDOG_G2_PC   pin the panel-ring depth / 32-channel chunks per operand stage
+//   LIDOG_G2_RING    0 = the ring shape of the first validated lean kernel (32 id slots, 3 weight stages when they fit)
+//   LIDOG_G2_T       pin the tiles per super-tile (parity tests sweep the multi-tile schedules on small inputs)
+//   LIDOG_WG_CTAS / LIDOG_WG_BATCH   wgrad CTA target / MMA-warp batch
+struct Switches {
+  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2;
+};
+static const Switches& switches() {
+  static const Switches sw = {env_int("LIDOG_DBG", 0),     env_int("LIDOG_ACC_SETS", 2), env_int("LIDOG_G2_OPT", 3),
+                              env_int("LIDOG_G2_SB", 0),   env_int("LIDOG_G2_PC", 0),    env_int("LIDOG_G2_RING", 1) != 0,
+                              env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
+                              env_int("LIDOG_G2_MMA2", 0)};
+  return sw;
+}
+
 // host launcher: forward / dgrad
 int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void* B16, int N, int flip_k, int fmt,
-                    const float* out_scale, const float* bias, float* Y, cudaStream_t stream) {
+                    const float* out_scale, const float* bias, float* Y, float* stats, cudaStream_t stream) {
   using namespace v2;
+  const Switches& sw = switches();
   int sm_count = 0;
   int* err = nullptr;
   int rc = tc_runtime(&sm_count, &err);
@@ -1021,6 +1062,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   g.plan = *plan;
   g.A = (const uint16_t*)A16;
   g.Y = Y;
+  g.stats = stats;
   g.out_scale = out_scale;
   g.bias = bias;
   g.Ck = Ck;
@@ -1031,15 +1073,16 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     set_error("lg_conv_gemm_tc: N=%d cannot be split into equal multiples of 16", N);
     return LG_ERR_UNSUPPORTED;
   }
-  g.flip = flip_k;
-  {
-    const char* e = getenv("LIDOG_DBG");
-    g.dbg = e ? atoi(e) : 0;
+  if (stats && g.n_blk % 32 != 0) {
+    set_error("lg_conv_layer_forward: epilogue statistics need column blocks that are multiples of 32 (N=%d)", N);
+    return LG_ERR_UNSUPPORTED;
   }
+  g.flip = flip_k;
+  g.dbg = sw.dbg;
   g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
   g.n_tiles = plan->n_slots / LG_TILE_ROWS;
   g.err = err;
-  rc = sched_slot(&g.sched);
+  rc = counter_slot(&g.sched);
   if (rc) return rc;
   if (n_split > 4) {
     set_error("lg_conv_gemm_tc: N=%d needs more than 4 column blocks", N);
@@ -1053,52 +1096,33 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   int T = 512 / g.n_blk;
   if (T > 8) T = 8;
   while (T > 1 && ceil_div(g.n_tiles, T) * n_split < 3 * (int64_t)sm_count) --T;
+  if (sw.force_t > 0 && sw.force_t < T) T = sw.force_t;
+  if (sw.force_t > T && sw.force_t <= 8 && sw.force_t * g.n_blk <= 512) T = sw.force_t;
   // two accumulator sets when that still leaves T >= 1 (LIDOG_ACC_SETS=1 forces the single-set schedule)
   g.sets = 1;
-  {
-    const char* e = getenv("LIDOG_ACC_SETS");
-    const int want = e ? atoi(e) : 2;
-    if (want == 2 && 2 * g.n_blk <= 512) {
-      g.sets = 2;
-      const int tmax = 512 / (2 * g.n_blk) < 4 ? 512 / (2 * g.n_blk) : 4;  // 2 * T accumulator barriers <= 8
-      if (T > tmax) T = tmax;
-    }
+  if (sw.acc_sets == 2 && 2 * g.n_blk <= 512) {
+    g.sets = 2;
+    const int tmax = 512 / (2 * g.n_blk) < 4 ? 512 / (2 * g.n_blk) : 4;  // 2 * T accumulator barriers <= 8
+    if (T > tmax) T = tmax;
   }
   g.T = T;
   g.n_super = ceil_div(g.n_tiles, T);
   // Pipeline shape.  The weight-panel ring gets 3 stages whenever 4 operand stages still fit next to it (with 2,
   // the TMA load of the next panel cannot start before the MMAs of the current one retire: the 256-channel
   // layers waited 22 % of the time for weights); the rest of the budget goes to operand (gather) stages.
-  // LIDOG_G2_SB / LIDOG_G2_PC pin the panel-ring depth / the 32-channel chunks per stage for experiments;
-  // LIDOG_G2_OPT bits: 2 = deep panel ring, 4 = L2 row prefetch (see k_gemm2).
-  int opt = 3;
-  {
-    const char* e = getenv("LIDOG_G2_OPT");
-    if (e) opt = atoi(e);
-  }
-  int force_sb = 0, force_pc = 0;
-  {
-    const char* e = getenv("LIDOG_G2_SB");
-    if (e) force_sb = atoi(e);
-    e = getenv("LIDOG_G2_PC");
-    if (e) force_pc = atoi(e);
-  }
+  const int opt = sw.opt;
+  const int force_sb = sw.force_sb, force_pc = sw.force_pc;
   if (force_pc > 0 && force_pc < g.pc) {
     int pc = force_pc;
     while (n_chunks % pc != 0) --pc;
     g.pc = pc;
     g.n_panels = n_chunks / pc;
   }
-  // LIDOG_G2_RING=0 restores the ring shape of the first validated lean kernel (32 id slots, 3 weight stages when
-  // they fit).  Default: the ncu source view of the lean kernel (profiles/r01_s4_gemm2_source_stalls.txt) shows the
-  // MMA warp polling the stage-full barrier ~17 times per unit and the producers waiting for free stages a quarter
-  // of the time -- a latency-bound ring -- so shared memory goes to operand stages first: 16 id slots (8 KB instead
-  // of 16) and 2 weight stages whenever that buys another operand stage.
-  static int ring_new = -1;
-  if (ring_new < 0) {
-    const char* e = getenv("LIDOG_G2_RING");
-    ring_new = (e && atoi(e) == 0) ? 0 : 1;
-  }
+  // Ring shape (LIDOG_G2_RING=0 restores 32 id slots / 3 weight stages).  The ncu source view of the lean kernel
+  // (profiles/r01_s4_gemm2_source_stalls.txt) shows the MMA warp polling the stage-full barrier ~17 times per unit
+  // and the producers waiting for free stages a quarter of the time -- a latency-bound ring -- so shared memory goes
+  // to operand stages first: 16 id slots (8 KB instead of 16) and 2 weight stages whenever that buys another stage.
+  const int ring_new = sw.ring_new;
   const int ni_slots = ring_new ? 4 * kProdWarps : 8 * kProdWarps;
   size_t stageA, stageB;
   for (;;) {
@@ -1149,30 +1173,28 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   rc = tc_make_tmap(&tmB, B16, (int64_t)plan->kernel_volume * N, Ck, g.n_blk);
   if (rc) return rc;
   dim3 grid((unsigned)(g.n_super < sm_count ? g.n_super : sm_count), (unsigned)n_split);
-  // production instantiation unless an experiment switch is set; one instantiation per stage width
-  // Issuers.  EXPERIMENTAL, off by default (LIDOG_G2_MMA2=1 enables it): tile-parity split for super-tiles of >= 2
-  // tiles, column halves for single tiles.  Measured on B200 after the MMA role was trimmed
-  // (profiles/r01_s4_sweep_h4_two_issuers.txt): -6 % on ts4 128->128, -4 % on ts4 64->64, nothing on the
-  // 256-channel layers -- the issuer is no longer what the kernel waits for.  The tile-parity mode trapped on the
-  // ts2 96->96 shape (5-stage ring): an issuer that skipped the other issuer's barrier phases could alias parities
-  // once it ran a ring wrap ahead; the waits now cover every phase (fix written after the GPU budget of the round
-  // was spent: NOT yet re-verified on hardware).  The single-issuer instantiation is the verified product path.
+  // One production instantiation per stage width.  The two-issuer modes (SPLIT 1 / 2) are EXPERIMENTAL and compiled
+  // only with -DLIDOG_EXPERIMENTAL (then LIDOG_G2_MMA2=1 selects them): measured <= 6 % where they ran, and the
+  // tile-parity mode trapped on one shape before the every-phase wait fix, which is unverified on hardware.
   int split = 0;
-  {
-    const char* e = getenv("LIDOG_G2_MMA2");
-    if (e && atoi(e) != 0) split = g.T >= 2 ? 1 : ((g.n_blk % 32 == 0) ? 2 : 0);
-  }
+#ifdef LIDOG_EXPERIMENTAL
+  if (sw.mma2) split = g.T >= 2 ? 1 : ((g.n_blk % 32 == 0) ? 2 : 0);
+#endif
 #define LG_LAUNCH_GEMM2(DBGV, PCV, SPV)                                                                                   \
   do {                                                                                                                     \
     LG_CUDA_OK(cudaFuncSetAttribute(k_gemm2<DBGV, PCV, SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     k_gemm2<DBGV, PCV, SPV><<<grid, kThreadsG2, smem, stream>>>(g, tmB);                                                   \
   } while (0)
+#ifdef LIDOG_EXPERIMENTAL
 #define LG_LAUNCH_GEMM2_SP(DBGV, PCV)                                                                                      \
   switch (split) {                                                                                                         \
     case 0: LG_LAUNCH_GEMM2(DBGV, PCV, 0); break;                                                                          \
     case 1: LG_LAUNCH_GEMM2(DBGV, PCV, 1); break;                                                                          \
     default: LG_LAUNCH_GEMM2(DBGV, PCV, 2); break;                                                                         \
   }
+#else
+#define LG_LAUNCH_GEMM2_SP(DBGV, PCV) LG_LAUNCH_GEMM2(DBGV, PCV, 0);
+#endif
 #define LG_LAUNCH_GEMM2_PC(DBGV)                                                                                           \
   switch (g.pc) {                                                                                                          \
     case 1: LG_LAUNCH_GEMM2_SP(DBGV, 1); break;                                                                            \
@@ -1180,6 +1202,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
     case 3: LG_LAUNCH_GEMM2_SP(DBGV, 3); break;                                                                            \
     default: LG_LAUNCH_GEMM2_SP(DBGV, 4); break;                                                                           \
   }
+  (void)split;
   if (g.dbg) {
     LG_LAUNCH_GEMM2_PC(true)
   } else {
@@ -1205,15 +1228,10 @@ static int wgrad2_shape(const lgConvPlan* plan, int Cin, int Cout, int* G, int* 
   // re-read by the reduction) and one pipeline ramp, so a chunk should own >= ~32 tiles; but the launch wants at
   // least one wave of 148 CTAs and gains nothing beyond four.  Measured (profiles/r01_s4_sweep_a.txt): the layers at
   // tensor stride >= 4 ran 1.3-1.8x faster with 148 CTAs than with 592, the stride-1 layers 1.3x slower.
-  // LIDOG_WG_CTAS pins the CTA target for experiments.
-  static int target_ctas = -1;
-  if (target_ctas < 0) {
-    const char* e = getenv("LIDOG_WG_CTAS");
-    target_ctas = e && atoi(e) > 0 ? atoi(e) : 0;
-  }
+  const int target_ctas = switches().wg_ctas;
   const int64_t per = (int64_t)*n_groups * m_blocks;
   int64_t want;
-  if (target_ctas) {
+  if (target_ctas > 0) {
     want = target_ctas / per;
   } else {
     const int64_t hi = 592 / per, lo = ceil_div((int64_t)148, per);
@@ -1259,8 +1277,7 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   while (g.sa > 2 && g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
   {
-    const char* e = getenv("LIDOG_WG_BATCH");
-    const int want = e ? atoi(e) : 4;
+    const int want = switches().wg_batch;
     g.bmax = want < 1 ? 1 : (want < g.sa ? want : g.sa);
   }
   const size_t smem = g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb);
@@ -1276,7 +1293,128 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
                                 dW, stream);
 }
 
+static int check_tc_plan(const lgConvPlan* p, const char* who) {
+  LG_CHECK_ARG(p != nullptr, "%s: null plan", who);
+  LG_CHECK_ARG(p->n_slots > 0 && p->n_slots % LG_TILE_ROWS == 0, "%s: n_slots must be a positive multiple of 128", who);
+  LG_CHECK_ARG(p->kernel_volume >= 1 && p->kernel_volume <= 128 && p->mask_words == (p->kernel_volume + 31) / 32,
+               "%s: bad kernel_volume/mask_words", who);
+  LG_CHECK_ARG(p->k_stride == 0 || p->k_stride == p->n_slots, "%s: k_stride must be 0 or n_slots", who);
+  LG_CHECK_ARG(p->nbr && p->tile_mask, "%s: null plan arrays", who);
+  LG_CHECK_ARG(p->n_in < ((int64_t)1 << 31) && p->n_out < ((int64_t)1 << 31), "%s: more than 2^31 rows", who);
+  return LG_OK;
+}
+
+static int check_gemm(const lgConvPlan* plan, int Ck, int N, int fmt, const char* who) {
+  int rc = check_tc_plan(plan, who);
+  if (rc) return rc;
+  if (Ck % 32 != 0 || N % 16 != 0 || N < 16 || N > 512) {
+    set_error("%s: Ck=%d must be a multiple of 32 and N=%d a multiple of 16 in [16,512]", who, Ck, N);
+    return LG_ERR_UNSUPPORTED;
+  }
+  // the gather kernels keep row byte offsets in 32 bits
+  if ((uint64_t)plan->n_in * (uint64_t)Ck * 2ull >= ((uint64_t)1 << 32)) {
+    set_error("%s: operand matrix of %lld x %d 16-bit elements exceeds the 4 GiB row-offset range", who,
+              (long long)plan->n_in, Ck);
+    return LG_ERR_UNSUPPORTED;
+  }
+  LG_CHECK_ARG(fmt == LG_FMT_BF16 || fmt == LG_FMT_FP16, "%s: bad format", who);
+  return LG_OK;
+}
+
+static int check_wgrad(const lgConvPlan* plan, int Cin, int Cout, int fmt, const char* who) {
+  int rc = check_tc_plan(plan, who);
+  if (rc) return rc;
+  if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cin < 32) {
+    set_error("%s: Cin=%d, Cout=%d must be multiples of 32 with Cout <= 256", who, Cin, Cout);
+    return LG_ERR_UNSUPPORTED;
+  }
+  if ((uint64_t)plan->n_in * (uint64_t)Cin * 2ull >= ((uint64_t)1 << 32) ||
+      (uint64_t)plan->n_out * (uint64_t)Cout * 2ull >= ((uint64_t)1 << 32)) {
+    set_error("%s: operand matrix exceeds the 4 GiB row-offset range", who);
+    return LG_ERR_UNSUPPORTED;
+  }
+  LG_CHECK_ARG(fmt == LG_FMT_BF16 || fmt == LG_FMT_FP16, "%s: bad format", who);
+  return LG_OK;
+}
+
 }  // namespace lg
+
+using namespace lg;
+
+extern "C" int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t Ck, const void* B16, int32_t N,
+                               int32_t flip_k, int32_t fmt, const float* out_scale, const float* bias, float* Y,
+                               int32_t gather_mode, void* stream_) {
+  int rc = check_gemm(plan, Ck, N, fmt, "lg_conv_gemm_tc");
+  if (rc) return rc;
+  LG_CHECK_ARG(A16 && B16 && Y, "lg_conv_gemm_tc: null pointer");
+  if (gather_mode != 2) {
+    set_error("lg_conv_gemm_tc: gather_mode %d is not in the library (the first-generation kernels live in "
+              "tools/legacy/conv_tc_gen1.cu as the record)", gather_mode);
+    return LG_ERR_UNSUPPORTED;
+  }
+  return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin, int32_t Cout) {
+  if (!plan || Cout < 32 || Cout > 256) return 0;
+  return wgrad_tc2_workspace(plan, Cin, Cout);
+}
+
+extern "C" int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const void* dY16, int32_t Cout,
+                                int32_t fmt, const float* out_scale, float* dW, int32_t gather_mode, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
+  int rc = check_wgrad(plan, Cin, Cout, fmt, "lg_conv_wgrad_tc");
+  if (rc) return rc;
+  LG_CHECK_ARG(X16 && dY16 && dW && workspace, "lg_conv_wgrad_tc: null pointer");
+  LG_CHECK_ARG(workspace_bytes >= lg_conv_wgrad_tc_workspace(plan, Cin, Cout), "lg_conv_wgrad_tc: workspace too small");
+  if (gather_mode != 2) {
+    set_error("lg_conv_wgrad_tc: gather_mode %d is not in the library", gather_mode);
+    return LG_ERR_UNSUPPORTED;
+  }
+  return launch_wgrad_tc2(plan, X16, Cin, dY16, Cout, fmt, out_scale, dW, workspace, (cudaStream_t)stream_);
+}
+
+/* One MinkowskiConvolution forward on the tensor-core path in one host call (see include/lidog_b200.h). */
+extern "C" int lg_conv_layer_forward(const lgConvPlan* plan, const void* X16, int32_t Cin, const float* W, int32_t Cout,
+                                     void* w16, void* w16t, int32_t prep, int32_t fmt, const float* bias, float* Y,
+                                     float* stat_partials, void* stream_) {
+  int rc = check_gemm(plan, Cin, Cout, fmt, "lg_conv_layer_forward");
+  if (rc) return rc;
+  LG_CHECK_ARG(X16 && w16t && Y && (!prep || W), "lg_conv_layer_forward: null pointer");
+  if (prep) {
+    rc = lg_prep_weights(W, plan->kernel_volume, Cin, Cout, w16, w16t, fmt, stream_);
+    if (rc) return rc;
+  }
+  return launch_gemm_tc2(plan, X16, Cin, w16t, Cout, 0, fmt, nullptr, bias, Y, stat_partials, (cudaStream_t)stream_);
+}
+
+/* dgrad and wgrad of one MinkowskiConvolution in one host call; the split-K partials live in the library arena. */
+extern "C" int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConvPlan* plan_wgrad, int32_t flip_dgrad,
+                                      const void* X16, int32_t Cin, const void* dY16, int32_t Cout, const void* w16,
+                                      int32_t fmt, const float* inv_scale, float* dX, float* dW, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc;
+  LG_CHECK_ARG(dY16, "lg_conv_layer_backward: null gradient");
+  if (dX) {
+    rc = check_gemm(plan_dgrad, Cout, Cin, fmt, "lg_conv_layer_backward(dgrad)");
+    if (rc) return rc;
+    LG_CHECK_ARG(w16, "lg_conv_layer_backward: null weights");
+    rc = launch_gemm_tc2(plan_dgrad, dY16, Cout, w16, Cin, flip_dgrad, fmt, inv_scale, nullptr, dX, nullptr, stream);
+    if (rc) return rc;
+  }
+  if (dW) {
+    rc = check_wgrad(plan_wgrad, Cin, Cout, fmt, "lg_conv_layer_backward(wgrad)");
+    if (rc) return rc;
+    LG_CHECK_ARG(X16, "lg_conv_layer_backward: null operand");
+    ArenaCursor ar;
+    const size_t ws = wgrad_tc2_workspace(plan_wgrad, Cin, Cout);
+    rc = arena_begin(stream, ws, &ar);
+    if (rc) return rc;
+    rc = launch_wgrad_tc2(plan_wgrad, X16, Cin, dY16, Cout, fmt, inv_scale, dW, arena_take(&ar, ws), stream);
+    if (rc) return rc;
+  }
+  return LG_OK;
+}
 
 // experiment hook (not part of the reference-facing ABI): per-role wait cycles of CTA 0, LIDOG_DBG & 8
 extern "C" int lg_debug_profile(long long* out16, int reset) { return lg::debug_profile(out16, reset); }

@@ -5,6 +5,7 @@
 // coordinate maps implied by MinkowskiConvolution(stride=2) (utils/models/minkunet_bev.py:62-83).
 // HBM-bound integer kernels: one coalesced pass over the rows per phase, table probes hit L2.
 #include "common.cuh"
+#include "runtime.cuh"
 #include "scan.cuh"
 
 namespace lg {
@@ -47,10 +48,14 @@ __device__ __forceinline__ int4 stride_coord(int4 c, int stride) {
 }
 
 // Phase 1: insert every row; the slot keeps the MINIMUM row id (= first occurrence).
+// (n_dev, when given, holds the true row count on the device -- the chained levels of lg_coords_pyramid never learn
+// their sizes on the host; n is then only the upper bound the grid was sized for)
 __global__ void __launch_bounds__(256)
-    k_insert(const int4* __restrict__ coords, int64_t n, int stride, HashSlot* __restrict__ table,
-             unsigned long long mask, int* __restrict__ slot_of_row, int* __restrict__ status) {
+    k_insert(const int4* __restrict__ coords, int64_t n, const int64_t* __restrict__ n_dev, int stride,
+             HashSlot* __restrict__ table, unsigned long long mask, int* __restrict__ slot_of_row,
+             int* __restrict__ status) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int4 c = stride_coord(coords[i], stride);
   if (!coord_in_range(c.x, c.y, c.z, c.w)) {
@@ -73,8 +78,10 @@ __global__ void __launch_bounds__(256)
 // Phase 2 (optional): a voxel whose points disagree on the label is marked.
 __global__ void __launch_bounds__(256)
     k_label_disagree(const int* __restrict__ slot_of_row, const HashSlot* __restrict__ table,
-                     const int32_t* __restrict__ labels, int64_t n, unsigned char* __restrict__ disagree) {
+                     const int32_t* __restrict__ labels, int64_t n, const int64_t* __restrict__ n_dev,
+                     unsigned char* __restrict__ disagree) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int s = slot_of_row[i];
   if (s < 0) return;
@@ -85,7 +92,9 @@ __global__ void __launch_bounds__(256)
 struct FirstFlag {
   const int* slot_of_row;
   const HashSlot* table;
+  const int64_t* n_dev;
   __device__ bool operator()(int64_t i) const {
+    if (n_dev && i >= *n_dev) return false;
     int s = slot_of_row[i];
     return s >= 0 && table[s].val == (unsigned)i;
   }
@@ -113,8 +122,10 @@ struct FirstSink {
 // Phase 4: inverse map (reads the table while it still holds first-row ids).
 __global__ void __launch_bounds__(256)
     k_inverse(const int* __restrict__ slot_of_row, const HashSlot* __restrict__ table,
-              const int* __restrict__ uid_of_first, int64_t n, int64_t* __restrict__ inverse_map) {
+              const int* __restrict__ uid_of_first, int64_t n, const int64_t* __restrict__ n_dev,
+              int64_t* __restrict__ inverse_map) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int s = slot_of_row[i];
   inverse_map[i] = (s >= 0) ? (int64_t)uid_of_first[table[s].val] : -1;
@@ -192,6 +203,42 @@ extern "C" int lg_quantize_points_f64(const double* points_xyz, const int32_t* b
 
 extern "C" size_t lg_coords_unique_workspace(int64_t n) { return carve_unique(nullptr, n > 0 ? n : 1).total; }
 
+namespace lg {
+// One level: unique (strided) coordinates of `n` rows (n_dev: device-side count, n = upper bound) + its hash table.
+static int unique_level(const int32_t* coords4, int64_t n, const int64_t* n_dev, int32_t stride, void* table,
+                        int64_t capacity, int32_t* out_coords4, int64_t* unique_map, int64_t* inverse_map,
+                        const int32_t* labels, int32_t ignore_label, int32_t* colabels, int64_t* count_status,
+                        void* workspace, cudaStream_t stream) {
+  LG_CUDA_OK(cudaMemsetAsync(table, 0xFF, lg_hash_bytes(capacity), stream));
+  LG_CUDA_OK(cudaMemsetAsync(count_status, 0, 2 * sizeof(int64_t), stream));
+  if (n == 0) return LG_OK;
+  UniqueWorkspace w = carve_unique(workspace, n);
+  LG_CUDA_OK(cudaMemsetAsync(w.status, 0, sizeof(int), stream));
+  const unsigned grid = (unsigned)ceil_div(n, 256);
+  HashSlot* tab = (HashSlot*)table;
+  k_insert<<<grid, 256, 0, stream>>>((const int4*)coords4, n, n_dev, stride, tab, (unsigned long long)(capacity - 1),
+                                     w.slot_of_row, w.status);
+  LG_LAUNCH_OK();
+  if (colabels) {
+    LG_CUDA_OK(cudaMemsetAsync(w.disagree, 0, (size_t)n, stream));
+    k_label_disagree<<<grid, 256, 0, stream>>>(w.slot_of_row, tab, labels, n, n_dev, w.disagree);
+    LG_LAUNCH_OK();
+  }
+  FirstFlag flag{w.slot_of_row, tab, n_dev};
+  FirstSink sink{(const int4*)coords4, stride,  (int4*)out_coords4, unique_map, w.uid_of_first,
+                 labels,               w.disagree, ignore_label,       colabels};
+  int rc = device_scan(flag, sink, n, count_status, w.scan, stream);
+  if (rc != LG_OK) return rc;
+  k_inverse<<<grid, 256, 0, stream>>>(w.slot_of_row, tab, w.uid_of_first, n, n_dev, inverse_map);
+  LG_LAUNCH_OK();
+  k_relabel<<<(unsigned)ceil_div(capacity, 256), 256, 0, stream>>>(tab, capacity, w.uid_of_first);
+  LG_LAUNCH_OK();
+  k_write_status<<<1, 1, 0, stream>>>(count_status, w.status);
+  LG_LAUNCH_OK();
+  return LG_OK;
+}
+}  // namespace lg
+
 extern "C" int lg_coords_unique(const int32_t* coords4, int64_t n, int32_t stride, void* table, int64_t capacity,
                                 int32_t* out_coords4, int64_t* unique_map, int64_t* inverse_map,
                                 const int32_t* labels, int32_t ignore_label, int32_t* colabels, int64_t* count_status,
@@ -202,34 +249,43 @@ extern "C" int lg_coords_unique(const int32_t* coords4, int64_t n, int32_t strid
                "lg_coords_unique: capacity must be a power of two >= max(1024, 2n)");
   LG_CHECK_ARG(table && count_status, "lg_coords_unique: null table/count_status");
   LG_CHECK_ARG((colabels == nullptr) || labels, "lg_coords_unique: colabels requested without labels");
-  LG_CUDA_OK(cudaMemsetAsync(table, 0xFF, lg_hash_bytes(capacity), stream));
-  LG_CUDA_OK(cudaMemsetAsync(count_status, 0, 2 * sizeof(int64_t), stream));
-  if (n == 0) return LG_OK;
-  LG_CHECK_ARG(coords4 && out_coords4 && unique_map && inverse_map && workspace, "lg_coords_unique: null pointer");
-  UniqueWorkspace w = carve_unique(workspace, n);
-  LG_CHECK_ARG(workspace_bytes >= w.total, "lg_coords_unique: workspace too small (%zu < %zu)", workspace_bytes,
-               w.total);
-  LG_CUDA_OK(cudaMemsetAsync(w.status, 0, sizeof(int), stream));
-  const unsigned grid = (unsigned)ceil_div(n, 256);
-  HashSlot* tab = (HashSlot*)table;
-  k_insert<<<grid, 256, 0, stream>>>((const int4*)coords4, n, stride, tab, (unsigned long long)(capacity - 1),
-                                     w.slot_of_row, w.status);
-  LG_LAUNCH_OK();
-  if (colabels) {
-    LG_CUDA_OK(cudaMemsetAsync(w.disagree, 0, (size_t)n, stream));
-    k_label_disagree<<<grid, 256, 0, stream>>>(w.slot_of_row, tab, labels, n, w.disagree);
-    LG_LAUNCH_OK();
+  if (n > 0) {
+    LG_CHECK_ARG(coords4 && out_coords4 && unique_map && inverse_map && workspace, "lg_coords_unique: null pointer");
+    const size_t need = carve_unique(nullptr, n).total;
+    LG_CHECK_ARG(workspace_bytes >= need, "lg_coords_unique: workspace too small (%zu < %zu)", workspace_bytes, need);
   }
-  FirstFlag flag{w.slot_of_row, tab};
-  FirstSink sink{(const int4*)coords4, stride,  (int4*)out_coords4, unique_map, w.uid_of_first,
-                 labels,               w.disagree, ignore_label,       colabels};
-  int rc = device_scan(flag, sink, n, count_status, w.scan, stream);
-  if (rc != LG_OK) return rc;
-  k_inverse<<<grid, 256, 0, stream>>>(w.slot_of_row, tab, w.uid_of_first, n, inverse_map);
-  LG_LAUNCH_OK();
-  k_relabel<<<(unsigned)ceil_div(capacity, 256), 256, 0, stream>>>(tab, capacity, w.uid_of_first);
-  LG_LAUNCH_OK();
-  k_write_status<<<1, 1, 0, stream>>>(count_status, w.status);
-  LG_LAUNCH_OK();
+  return unique_level(coords4, n, nullptr, stride, table, capacity, out_coords4, unique_map, inverse_map, labels,
+                      ignore_label, colabels, count_status, workspace, stream);
+}
+
+/* Every coordinate level of a batch in ONE call and without a host round trip between the levels (see the header). */
+extern "C" int lg_coords_pyramid(const int32_t* coords4, int64_t n, const int32_t* labels, int32_t ignore_label,
+                                 int32_t* colabels, int32_t n_levels, const int32_t* strides, const lgLevelOut* levels,
+                                 int64_t* counts_dev, int64_t* counts_host, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LG_CHECK_ARG(n >= 1 && n_levels >= 1 && n_levels <= 8 && strides && levels && counts_dev && coords4,
+               "lg_coords_pyramid: bad arguments");
+  LG_CHECK_ARG((colabels == nullptr) || labels, "lg_coords_pyramid: colabels requested without labels");
+  for (int l = 0; l < n_levels; ++l) {
+    const lgLevelOut& L = levels[l];
+    LG_CHECK_ARG(strides[l] >= 1 && (l == 0 || strides[l] > strides[l - 1]), "lg_coords_pyramid: strides must increase");
+    LG_CHECK_ARG(L.table && L.coords4 && L.unique_map && L.inverse_map && L.capacity >= 2 * n &&
+                     (L.capacity & (L.capacity - 1)) == 0 && L.capacity >= 1024,
+                 "lg_coords_pyramid: level %d needs table / outputs for the upper bound of %lld rows", l, (long long)n);
+  }
+  ArenaCursor ar;
+  const size_t ws = carve_unique(nullptr, n).total;
+  int rc = arena_begin(stream, ws, &ar);
+  if (rc) return rc;
+  void* workspace = arena_take(&ar, ws);
+  for (int l = 0; l < n_levels; ++l) {
+    const lgLevelOut& L = levels[l];
+    rc = unique_level(l == 0 ? coords4 : levels[l - 1].coords4, n, l == 0 ? nullptr : counts_dev + 2 * (l - 1),
+                      strides[l], L.table, L.capacity, L.coords4, L.unique_map, L.inverse_map, l == 0 ? labels : nullptr,
+                      ignore_label, l == 0 ? colabels : nullptr, counts_dev + 2 * l, workspace, stream);
+    if (rc) return rc;
+  }
+  if (counts_host)
+    LG_CUDA_OK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int64_t) * 2 * n_levels, cudaMemcpyDeviceToHost, stream));
   return LG_OK;
 }

@@ -11,36 +11,10 @@
 // reads) has finished, so with kSlots >= 2 no slot is overwritten while a peer may still read it.
 // The spin is bounded: a missing peer traps the kernel instead of hanging the GPU.
 #include "common.cuh"
+#include "peer.cuh"
+#include "runtime.cuh"
 
 namespace lg {
-
-constexpr int kPeerSlots = 4;
-constexpr int kPeerMaxN = 3 * 1024 + 8;
-constexpr int kPeerMaxWorld = 16;
-
-struct PeerSlot {
-  unsigned long long flag;
-  unsigned long long pad;
-  double data[kPeerMaxN];
-};
-
-struct PeerTable {
-  PeerSlot* buf[kPeerMaxWorld];
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(1024)
     k_peer_sum(const double* __restrict__ local, int n, PeerTable tab, int world, int rank, unsigned long long epoch,
@@ -71,8 +45,6 @@ __global__ void __launch_bounds__(1024)
     out[i] = a;
   }
 }
-
-int tc_runtime(int* sm_count, int** err_word);
 
 }  // namespace lg
 

@@ -19,25 +19,28 @@ from ._grad16 import take_grad16
 from .sparse_tensor import SparseTensor
 
 # operand format of the tensor-core path: "fp16" (default; 2^-11 unit round-off meets the 1e-3 bar),
-# "bf16", or "off" (SIMT fp32 everywhere).  TC_GATHER: 2 = super-tile pipeline with cp.async row gathers
-# arriving on mbarriers (default, csrc/conv_tc2.cu); 0 = first-generation cp.async; 1 = TMA tile::gather4
-# (kept for the record: measured 2.7x slower than cp.async on B200, profiles/).
+# "bf16", or "off" (SIMT fp32 everywhere).
 CONFIG = {
     "tc": os.environ.get("LIDOG_TC", "fp16"),
-    "gather": int(os.environ.get("LIDOG_TC_GATHER", "2")),
     # mask-sorted gather plans (lg_kernel_map_sorted) for the 3x3x3 and stride-2 layers; 0 = natural row order
     "sorted": int(os.environ.get("LIDOG_SORTED_PLANS", "1")),
+    # the GEMM epilogue also writes per-tile column sums / sums of squares for the batch norm that follows
+    # (lg_conv_layer_forward's stat_partials): the statistics pass over the convolution output disappears
+    "epi_stats": int(os.environ.get("LIDOG_EPI_STATS", "1")),
+    # 1 = one library call per layer each way (lg_conv_layer_forward / _backward); 0 = the fine-grained entry points
+    # (lg_prep_weights + lg_conv_gemm_tc + lg_conv_wgrad_tc, workspaces from torch) kept for A/B runs
+    "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1")),
 }
+GATHER_MODE = 2  # the only pipeline in the library (include/lidog_b200.h, lg_conv_gemm_tc)
 
 
-# bench.py instrumentation: per-launch CUDA events + algorithmic FLOPs (2 * pairs * Cin * Cout).
-# A census pass (events=False) counts the pairs of every plan once; timed passes look them up by key.
+# Instrumentation for bench.py / tools (never on in a timed headline loop): per-launch CUDA events + algorithmic FLOPs
+# (2 * pairs * Cin * Cout).  A census pass (events=False) counts the pairs of every plan once; an instrumented pass
+# (events=True) brackets every launch with events and looks the pairs up by key.
 PROFILE = {"enabled": False, "events": False, "records": [], "pairs": {}}
 
 
 def _profiled(kernel, plan, cin, cout, launch):
-    if not PROFILE["enabled"]:
-        return launch()
     if not PROFILE["events"]:
         if plan.key not in PROFILE["pairs"]:
             PROFILE["pairs"][plan.key] = plan.count_pairs()
@@ -62,59 +65,112 @@ def _tc_ok(cin, cout):
     return _fmt() is not None and cin % 32 == 0 and cout % 32 == 0
 
 
+def _dt16(fmt):
+    return torch.float16 if fmt == cabi.FMT_FP16 else torch.bfloat16
+
+
 def _cast16(x: torch.Tensor, fmt: int, scale: torch.Tensor | None = None) -> torch.Tensor:
-    out = torch.empty(x.shape, dtype=torch.float16 if fmt == cabi.FMT_FP16 else torch.bfloat16, device=x.device)
-    cabi.check(cabi.lib().lg_cast_rows(cabi.ptr(x), cabi.ptr(out), x.numel(), fmt, cabi.ptr(scale), cabi.stream()),
+    out = torch.empty(x.shape, dtype=_dt16(fmt), device=x.device)
+    cabi.check(cabi.lib().lg_cast_rows(cabi.ptr(x), cabi.ptr(out), x.numel(), fmt, cabi.ptr(scale), cabi.stream_of(x)),
                "lg_cast_rows")
     return out
 
 
 def _gemm_simt(plan, A, W3, N, w_transposed, flip, bias):
     Y = torch.empty((plan.n_out, N), dtype=torch.float32, device=A.device)
-    cabi.check(cabi.lib().lg_conv_gemm_simt(plan.c, cabi.ptr(A), A.shape[1], cabi.ptr(W3), N, w_transposed, flip,
-                                            cabi.ptr(bias), cabi.ptr(Y), cabi.stream()), "lg_conv_gemm_simt")
+    cabi.check(cabi.lib().lg_conv_gemm_simt(plan.cref, cabi.ptr(A), A.shape[1], cabi.ptr(W3), N, w_transposed, flip,
+                                            cabi.ptr(bias), cabi.ptr(Y), cabi.stream_of(A)), "lg_conv_gemm_simt")
     return Y
 
 
 def _gemm_tc(plan, A16, B16, N, flip, fmt, out_scale, bias):
+    """Fine-grained path (LIDOG_LAYER_CALLS=0, instrumented passes, tools)."""
     Y = torch.empty((plan.n_out, N), dtype=torch.float32, device=A16.device)
 
     def launch():
-        cabi.check(cabi.lib().lg_conv_gemm_tc(plan.c, cabi.ptr(A16), A16.shape[1], cabi.ptr(B16), N, flip, fmt,
-                                              cabi.ptr(out_scale), cabi.ptr(bias), cabi.ptr(Y), CONFIG["gather"],
-                                              cabi.stream()), "lg_conv_gemm_tc")
-    _profiled("k_gemm_tc", plan, A16.shape[1], N, launch)
+        cabi.check(cabi.lib().lg_conv_gemm_tc(plan.cref, cabi.ptr(A16), A16.shape[1], cabi.ptr(B16), N, flip, fmt,
+                                              cabi.ptr(out_scale), cabi.ptr(bias), cabi.ptr(Y), GATHER_MODE,
+                                              cabi.stream_of(A16)), "lg_conv_gemm_tc")
+    if PROFILE["enabled"]:
+        _profiled("k_gemm_tc", plan, A16.shape[1], N, launch)
+    else:
+        launch()
     return Y
+
+
+class WeightCache:
+    """16-bit copies of one layer's kernel, refreshed only when the parameter changed (optimizer step, load):
+    round 1 ran lg_prep_weights for all 61 layers on every forward."""
+    __slots__ = ("key", "w16", "w16t")
+
+    def __init__(self):
+        self.key = None
+
+    def get(self, kernel: torch.Tensor, K, cin, cout, fmt):
+        """-> (w16 [K][Cin][Cout], w16t [K][Cout][Cin], stale) -- `stale` = the copies must be rewritten."""
+        key = (kernel._version, kernel.data_ptr(), fmt)
+        stale = key != self.key
+        if stale:
+            if self.key is None or self.w16.device != kernel.device or self.key[2] != fmt:
+                dt = _dt16(fmt)
+                self.w16 = torch.empty((K, cin, cout), dtype=dt, device=kernel.device)
+                self.w16t = torch.empty((K, cout, cin), dtype=dt, device=kernel.device)
+            self.key = key
+        return self.w16, self.w16t, stale
 
 
 class SparseConvFunction(torch.autograd.Function):
     """y = conv(x, kernel) over the gather plans of one layer.
 
     plans = (fwd, dgrad, wgrad, flip_dgrad): see MinkowskiConvolutionBase._plans.
+    `src` (optional SparseTensor) provides the cached 16-bit operand copy of x, `wcache` the cached 16-bit weights,
+    `box` (dict) receives the epilogue statistics for the batch norm that follows ("stats": [4 * tiles, 2 * Cout]).
     """
 
     @staticmethod
-    def forward(ctx, x, kernel, bias, plans, x16_cache):
+    def forward(ctx, x, kernel, bias, plans, src, wcache, box):
         p_fwd = plans[0]
-        W3 = kernel if kernel.dim() == 3 else kernel.unsqueeze(0)
-        K, cin, cout = W3.shape
+        if kernel.dim() == 3:
+            K, cin, cout = kernel.shape
+        else:
+            K, (cin, cout) = 1, kernel.shape
         x = x.contiguous()
-        W3c = W3.detach().contiguous()
-        b = None if bias is None else bias.detach().reshape(-1).contiguous()
         ctx.plans, ctx.shape, ctx.kdim = plans, (K, cin, cout), kernel.dim()
         ctx.has_bias = bias is not None
         ctx.tc = _tc_ok(cin, cout) and x.shape[0] > 0
+        L = cabi.lib()
         if ctx.tc:
             fmt = _fmt()
-            x16 = x16_cache(fmt) if x16_cache is not None else _cast16(x.detach(), fmt)
-            w16 = torch.empty((K, cin, cout), dtype=x16.dtype, device=x.device)
-            w16t = torch.empty((K, cout, cin), dtype=x16.dtype, device=x.device)
-            cabi.check(cabi.lib().lg_prep_weights(cabi.ptr(W3c), K, cin, cout, cabi.ptr(w16), cabi.ptr(w16t), fmt,
-                                                  cabi.stream()), "lg_prep_weights")
-            y = _gemm_tc(p_fwd, x16, w16t, cout, 0, fmt, None, b)
+            x16 = src._f16(fmt) if src is not None else _cast16(x.detach(), fmt)
+            Wc = kernel.detach()
+            if not Wc.is_contiguous():
+                Wc = Wc.contiguous()
+            b = None if bias is None else bias.detach().reshape(-1)
+            if wcache is None:
+                wcache = WeightCache()
+            w16, w16t, stale = wcache.get(Wc, K, cin, cout, fmt)
+            if CONFIG["layer_calls"] and not PROFILE["enabled"]:
+                y = torch.empty((p_fwd.n_out, cout), dtype=torch.float32, device=x.device)
+                stats = None
+                if box is not None and CONFIG["epi_stats"] and b is None:
+                    stats = torch.empty((4 * p_fwd.n_tiles, 2 * cout), dtype=torch.float32, device=x.device)
+                    box["stats"] = stats
+                cabi.check(L.lg_conv_layer_forward(p_fwd.cref, x16.data_ptr(), cin, Wc.data_ptr(), cout, w16.data_ptr(),
+                                                   w16t.data_ptr(), 1 if stale else 0, fmt, cabi.ptr(b), y.data_ptr(),
+                                                   cabi.ptr(stats), cabi.stream_of(x)), "lg_conv_layer_forward")
+                cabi.count_launches("lg_conv_layer_forward", 2 if stale else 1)
+            else:
+                if stale:
+                    cabi.check(L.lg_prep_weights(Wc.data_ptr(), K, cin, cout, w16.data_ptr(), w16t.data_ptr(), fmt,
+                                                 cabi.stream_of(x)), "lg_prep_weights")
+                y = _gemm_tc(p_fwd, x16, w16t, cout, 0, fmt, None, b)
+            # `kernel` is saved for autograd's version check only: a parameter update between this forward and its
+            # backward (which would also have refreshed the cached 16-bit copy) then fails loudly
             ctx.fmt, ctx.w16 = fmt, w16
-            ctx.save_for_backward(x16)
+            ctx.save_for_backward(x16, kernel)
         else:
+            W3c = (kernel if kernel.dim() == 3 else kernel.unsqueeze(0)).detach().contiguous()
+            b = None if bias is None else bias.detach().reshape(-1).contiguous()
             y = _gemm_simt(p_fwd, x.detach(), W3c, cout, 0, 0, b)
             ctx.save_for_backward(x.detach(), W3c)
         return y
@@ -129,8 +185,9 @@ class SparseConvFunction(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0, keepdim=True)
         if ctx.tc:
-            (x16,) = ctx.saved_tensors
+            x16, _ = ctx.saved_tensors
             fmt = ctx.fmt
+            w16 = ctx.w16
             hit = take_grad16(dy, fmt)  # the fused BN backward already wrote the scaled 16-bit gradient
             if hit is not None:
                 dy16, scale = hit
@@ -138,33 +195,50 @@ class SparseConvFunction(torch.autograd.Function):
                 scale = None
                 if fmt == cabi.FMT_FP16:  # bring the gradient into fp16's normal range (power-of-two scale)
                     scale = torch.empty(4, dtype=torch.float32, device=dy.device)
-                    cabi.check(L.lg_absmax_scale(cabi.ptr(dy), dy.numel(), cabi.ptr(scale), cabi.stream()),
+                    cabi.check(L.lg_absmax_scale(cabi.ptr(dy), dy.numel(), cabi.ptr(scale), cabi.stream_of(dy)),
                                "lg_absmax_scale")
                 dy16 = _cast16(dy, fmt, scale)
-            inv = None if scale is None else scale[1:]
-            if ctx.needs_input_grad[0]:
-                dx = _gemm_tc(p_dgrad, dy16, ctx.w16, cin, flip, fmt, inv, None)
-            if ctx.needs_input_grad[1]:
-                dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
-                ws_bytes = L.lg_conv_wgrad_tc_workspace(p_wgrad.c, cin, cout)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
-                _profiled("k_wgrad_tc", p_wgrad, cin, cout, lambda: cabi.check(
-                    L.lg_conv_wgrad_tc(p_wgrad.c, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt, cabi.ptr(inv),
-                                       cabi.ptr(dw), CONFIG["gather"], cabi.ptr(ws), ws_bytes, cabi.stream()),
-                    "lg_conv_wgrad_tc"))
+            inv_ptr = None if scale is None else scale.data_ptr() + 4  # scale = {2^k, 2^-k, ...}
+            want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            if CONFIG["layer_calls"] and not PROFILE["enabled"]:
+                if want_dx:
+                    dx = torch.empty((p_dgrad.n_out, cin), dtype=torch.float32, device=dy.device)
+                if want_dw:
+                    dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
+                cabi.check(L.lg_conv_layer_backward(p_dgrad.cref, p_wgrad.cref, flip, x16.data_ptr(), cin,
+                                                    dy16.data_ptr(), cout, w16.data_ptr(), fmt, inv_ptr, cabi.ptr(dx),
+                                                    cabi.ptr(dw), cabi.stream_of(dy)), "lg_conv_layer_backward")
+                cabi.count_launches("lg_conv_layer_backward", (1 if want_dx else 0) + (2 if want_dw else 0))
+            else:
+                inv = None if scale is None else scale[1:]
+                if want_dx:
+                    dx = _gemm_tc(p_dgrad, dy16, w16, cin, flip, fmt, inv, None)
+                if want_dw:
+                    dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
+                    ws_bytes = L.lg_conv_wgrad_tc_workspace(p_wgrad.cref, cin, cout)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
+
+                    def launch():
+                        cabi.check(L.lg_conv_wgrad_tc(p_wgrad.cref, cabi.ptr(x16), cin, cabi.ptr(dy16), cout, fmt,
+                                                      cabi.ptr(inv), cabi.ptr(dw), GATHER_MODE, cabi.ptr(ws), ws_bytes,
+                                                      cabi.stream_of(dy)), "lg_conv_wgrad_tc")
+                    if PROFILE["enabled"]:
+                        _profiled("k_wgrad_tc", p_wgrad, cin, cout, launch)
+                    else:
+                        launch()
         else:
             x, W3c = ctx.saved_tensors
             if ctx.needs_input_grad[0]:
                 dx = _gemm_simt(p_dgrad, dy, W3c, cin, 1, flip, None)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
-                ws_bytes = L.lg_conv_wgrad_workspace(p_wgrad.c, cin, cout)
+                ws_bytes = L.lg_conv_wgrad_workspace(p_wgrad.cref, cin, cout)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
-                cabi.check(L.lg_conv_wgrad_simt(p_wgrad.c, cabi.ptr(x), cin, cabi.ptr(dy), cout, cabi.ptr(dw),
-                                                cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_conv_wgrad_simt")
+                cabi.check(L.lg_conv_wgrad_simt(p_wgrad.cref, cabi.ptr(x), cin, cabi.ptr(dy), cout, cabi.ptr(dw),
+                                                cabi.ptr(ws), ws_bytes, cabi.stream_of(dy)), "lg_conv_wgrad_simt")
         if dw is not None and ctx.kdim == 2:
             dw = dw[0]
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class MinkowskiConvolutionBase(nn.Module):
@@ -186,6 +260,7 @@ class MinkowskiConvolutionBase(nn.Module):
         shape = (in_channels, out_channels) if self.kernel_volume == 1 else (self.kernel_volume, in_channels, out_channels)
         self.kernel = nn.Parameter(torch.empty(shape))
         self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+        self._wcache = WeightCache()
         self.reset_parameters()
 
     def reset_parameters(self, is_transpose=None):
@@ -225,8 +300,12 @@ class MinkowskiConvolutionBase(nn.Module):
         assert isinstance(input, SparseTensor)
         cm = input.coordinate_manager
         ts_out, plans = self._plans(cm, input._ts)
-        y = SparseConvFunction.apply(input.F, self.kernel, self.bias, plans, input._f16)
-        return SparseTensor(y, tensor_stride=ts_out, coordinate_manager=cm)
+        box = {} if self.training else None
+        y = SparseConvFunction.apply(input.F, self.kernel, self.bias, plans, input, self._wcache, box)
+        out = SparseTensor(y, tensor_stride=ts_out, coordinate_manager=cm)
+        if box:
+            out._stat_partials = (box["stats"], y._version)
+        return out
 
     def __repr__(self):
         return (f"{self.__class__.__name__}(in={self.in_channels}, out={self.out_channels}, "

@@ -9,6 +9,8 @@ arithmetic happens in liblidog_b200 (csrc/coords.cu, csrc/kmap.cu).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from .. import cabi
@@ -16,7 +18,7 @@ from . import _grad16
 
 
 def _check_count(count_status: torch.Tensor, what: str) -> int:
-    n, status = count_status.tolist()  # one host sync per coordinate level
+    n, status = count_status.tolist()  # one host sync
     if status != 0:
         raise RuntimeError(f"{what}: coordinate outside the packed-key range "
                            f"(|x|,|y|,|z| < 32768, 0 <= batch < 32768); status {status}")
@@ -24,7 +26,8 @@ def _check_count(count_status: torch.Tensor, what: str) -> int:
 
 
 def coords_unique(coords: torch.Tensor, stride: int = 1, labels: torch.Tensor | None = None, ignore_label: int = -100):
-    """Wrapper of lg_coords_unique -> dict(coords, unique_map, inverse_map, colabels, table, capacity, n)."""
+    """Wrapper of lg_coords_unique -> dict(coords, unique_map, inverse_map, colabels, table, capacity, n).
+    One level, one host sync; the training path builds all its levels at once with `build_levels`."""
     assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 4
     coords = coords.contiguous()
     L = cabi.lib()
@@ -43,11 +46,71 @@ def coords_unique(coords: torch.Tensor, stride: int = 1, labels: torch.Tensor | 
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     cabi.check(L.lg_coords_unique(cabi.ptr(coords), n, stride, cabi.ptr(table), cap, cabi.ptr(out_coords),
                                   cabi.ptr(unique_map), cabi.ptr(inverse_map), cabi.ptr(labels), ignore_label,
-                                  cabi.ptr(colabels), cabi.ptr(count), cabi.ptr(ws), ws_bytes, cabi.stream()),
+                                  cabi.ptr(colabels), cabi.ptr(count), cabi.ptr(ws), ws_bytes, cabi.stream_of(coords)),
                "lg_coords_unique")
     nu = _check_count(count, "lg_coords_unique")
     return dict(coords=out_coords[:nu], unique_map=unique_map[:nu], inverse_map=inverse_map[:n],
                 colabels=None if colabels is None else colabels[:nu], table=table, capacity=cap, n=nu)
+
+
+# Tensor strides built together with the stride-1 level (MinkUNet34's encoder: minkunet_bev.py:62,69,76,83).
+# Anything else is still derived on demand by `CoordinateManager.level` (one host round trip each).
+PREBUILD_STRIDES = (2, 4, 8, 16)
+_PINNED = {}
+
+
+def build_levels(coords: torch.Tensor, labels: torch.Tensor | None = None, ignore_label: int = -100,
+                 strides=(1,) + PREBUILD_STRIDES):
+    """All coordinate levels of a batch with ONE library call and ONE host synchronisation (lg_coords_pyramid): the
+    row count of a level reaches the next one on the device.  Returns a list of per-level dicts like `coords_unique`
+    (level 0 also carries colabels); `inverse_map` of level l > 0 maps the rows of level l-1 to level l."""
+    assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 4
+    n = coords.shape[0]
+    if n == 0:  # degenerate batch: the single-level call handles the empty case
+        res = [coords_unique(coords, strides[0], labels, ignore_label)]
+        for s in strides[1:]:
+            res.append(coords_unique(res[-1]["coords"], s))
+        return res
+    coords = coords.contiguous()
+    L = cabi.lib()
+    dev = coords.device
+    nl = len(strides)
+    cap = L.lg_hash_capacity(n)
+    tbytes = L.lg_hash_bytes(cap)
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int32).contiguous()
+    colabels = torch.empty(n, dtype=torch.int32, device=dev) if labels is not None else None
+    arrays, outs = [], (cabi.LevelOut * nl)()
+    for l in range(nl):
+        table = torch.empty(tbytes, dtype=torch.uint8, device=dev)
+        oc = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        maps = torch.empty((2, n), dtype=torch.int64, device=dev)
+        arrays.append((table, oc, maps))
+        outs[l] = cabi.LevelOut(table.data_ptr(), cap, oc.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr())
+    counts = torch.empty(2 * nl, dtype=torch.int64, device=dev)
+    key = (dev.index, nl)
+    host = _PINNED.get(key)
+    if host is None:
+        host = _PINNED[key] = torch.empty(2 * nl, dtype=torch.int64).pin_memory()
+    stream = cabi.stream_of(coords)
+    cabi.check(L.lg_coords_pyramid(coords.data_ptr(), n, cabi.ptr(labels), ignore_label, cabi.ptr(colabels), nl,
+                                   (C.c_int32 * nl)(*strides), outs, counts.data_ptr(), host.data_ptr(), stream),
+               "lg_coords_pyramid")
+    cabi.count_launches("lg_coords_pyramid", 7 * nl + (1 if labels is not None else 0))
+    torch.cuda.current_stream(dev).synchronize()  # the one host round trip of the step's coordinate work
+    cs = host.tolist()
+    res, n_in = [], n
+    for l in range(nl):
+        nu, status = int(cs[2 * l]), cs[2 * l + 1]
+        if status != 0:
+            raise RuntimeError(f"lg_coords_pyramid: coordinate outside the packed-key range at stride {strides[l]} "
+                               f"(|x|,|y|,|z| < 32768, 0 <= batch < 32768); status {status}")
+        table, oc, maps = arrays[l]
+        res.append(dict(coords=oc[:nu], unique_map=maps[0, :nu], inverse_map=maps[1, :n_in],
+                        colabels=colabels[:nu] if (l == 0 and colabels is not None) else None, table=table,
+                        capacity=cap, n=nu, stride=strides[l]))
+        n_in = nu
+    return res
 
 
 class Level:
@@ -66,6 +129,8 @@ class GatherPlan:
         self.nbr, self.out_row, self.tile_mask = nbr, out_row, tile_mask
         self.K, self.n_slots, self.n_out, self.n_in, self.k_stride = K, n_slots, n_out, n_in, k_stride
         self.c = cabi.make_plan(nbr, k_stride, out_row, tile_mask, K, n_slots, n_out, n_in)
+        self.cref = C.byref(self.c)  # what the entry points take; built once, not per call
+        self.n_tiles = n_slots // cabi.TILE
         self.key = None
 
     def count_pairs(self) -> int:
@@ -80,26 +145,35 @@ def _round_up(a, b):
 class CoordinateManager:
     def __init__(self, coordinates: torch.Tensor):
         _grad16.clear()  # a new batch: no gradient of the previous one is still wanted
-        res = coords_unique(coordinates, 1)
         self.device = coordinates.device
-        self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}
-        self.input_unique_map = res["unique_map"]
-        self.input_inverse_map = res["inverse_map"]
-        self.had_duplicates = res["n"] != coordinates.shape[0]
+        self._adopt(build_levels(coordinates), coordinates.shape[0])
+
+    def _adopt(self, levels, n_input):
+        first = levels[0]
+        self.levels = {}
+        for lv in levels:
+            ts = lv.get("stride", 1)
+            self.levels[ts] = Level(lv["coords"], lv["table"], lv["capacity"],
+                                    parent_of_finer=None if lv is first else lv["inverse_map"])
+        self.input_unique_map = first["unique_map"]
+        self.input_inverse_map = first["inverse_map"]
+        self.had_duplicates = first["n"] != n_input
         self.plans = {}
 
     @classmethod
-    def from_quantized(cls, res: dict):
-        """Adopt the table built by sparse_quantize(_batch): voxelisation and the network share ONE
-        hashed voxel index (no second hash build for ME.SparseTensor)."""
+    def from_quantized(cls, res):
+        """Adopt the tables built by sparse_quantize_batch: voxelisation and the network share ONE hashed voxel
+        index (no second hash build for ME.SparseTensor).  `res` = the level list of `build_levels`, or the dict of a
+        single `coords_unique` call."""
         _grad16.clear()
         self = cls.__new__(cls)
-        self.device = res["coords"].device
-        self.levels = {1: Level(res["coords"], res["table"], res["capacity"])}
-        self.input_unique_map, self.input_inverse_map = res["unique_map"], res["inverse_map"]
-        self.had_duplicates = False
-        self.plans = {}
+        levels = res["levels"] if isinstance(res, dict) and "levels" in res else ([res] if isinstance(res, dict) else res)
+        self.device = levels[0]["coords"].device
+        self._adopt(levels, levels[0]["n"])
         return self
+
+    def _stream(self):
+        return torch._C._cuda_getCurrentRawStream(self.device.index)
 
     # ------------------------------------------------------------------ coordinate levels
     def level(self, ts: int) -> Level:
@@ -130,7 +204,7 @@ class CoordinateManager:
         nbr = torch.empty((K, max(n_slots, 1)), dtype=torch.int32, device=self.device)
         mask = torch.empty((max(n_slots // cabi.TILE, 1), (K + 31) // 32), dtype=torch.int32, device=self.device)
         cabi.check(L.lg_kernel_map(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out, ksize,
-                                   scale, cabi.ptr(nbr), n_slots, cabi.ptr(mask), cabi.stream()), "lg_kernel_map")
+                                   scale, cabi.ptr(nbr), n_slots, cabi.ptr(mask), self._stream()), "lg_kernel_map")
         return GatherPlan(nbr, n_slots, None, mask, K, n_slots, n_out, lvl_in.n)
 
     def _sorted_plan(self, lvl_in: Level, lvl_out: Level, ksize: int, scale: int) -> GatherPlan:
@@ -147,7 +221,7 @@ class CoordinateManager:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         cabi.check(L.lg_kernel_map_sorted(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out,
                                           ksize, scale, cabi.ptr(nbr), cabi.ptr(out_row), n_slots, cabi.ptr(mask),
-                                          cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_kernel_map_sorted")
+                                          cabi.ptr(ws), ws_bytes, self._stream()), "lg_kernel_map_sorted")
         return GatherPlan(nbr, n_slots, out_row, mask, K, n_slots, n_out, lvl_in.n)
 
     def _plan_same(self, ts_in, ts_out, ksize):
@@ -183,7 +257,7 @@ class CoordinateManager:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         cabi.check(L.lg_kernel_map_up2(cabi.ptr(fine.coords), cabi.ptr(coarse.parent_of_finer), n_fine, ts_out,
                                        cabi.ptr(gather), cabi.ptr(out_row), cabi.ptr(mask), n_slots, cabi.ptr(used),
-                                       cabi.ptr(ws), ws_bytes, cabi.stream()), "lg_kernel_map_up2")
+                                       cabi.ptr(ws), ws_bytes, self._stream()), "lg_kernel_map_up2")
         return GatherPlan(gather, 0, out_row, mask, 8, n_slots, n_fine, coarse.n)
 
     def _plan_identity(self, ts_in, ts_out, ksize):
@@ -208,7 +282,7 @@ class CoordinateManager:
         ws_bytes = L.lg_scan_workspace(total)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         cabi.check(L.lg_kernel_map_pairs(cabi.ptr(plan.nbr), plan.K, plan.n_slots, cabi.ptr(in_rows),
-                                         cabi.ptr(out_rows), cabi.ptr(k_off), cabi.ptr(ws), ws_bytes, cabi.stream()),
+                                         cabi.ptr(out_rows), cabi.ptr(k_off), cabi.ptr(ws), ws_bytes, self._stream()),
                    "lg_kernel_map_pairs")
         k_off = k_off.cpu()
         p = int(k_off[-1])

@@ -30,7 +30,12 @@ import torch.nn as nn
 from .. import cabi
 from .sparse_tensor import SparseTensor
 
-CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1"))}
+import ctypes as _C
+
+CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1")),
+          # 1 = one library call per layer each way (lg_bn_layer_forward / _backward); 0 = fine-grained calls
+          "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1"))}
+C_byref = _C.byref
 
 from ._grad16 import publish_grad16
 
@@ -94,7 +99,95 @@ def _bn_statistics(x: torch.Tensor, bn, ws, ws_bytes):
 
 
 class FusedBNFunction(torch.autograd.Function):
-    """y = act(BN_a(x) [+ BN_b(x2)] [+ res]); also returns nothing else -- the 16-bit copy of y travels in `box`."""
+    """y = act(BN_a(x) [+ BN_b(x2)] [+ res]) with ONE library call each way (lg_bn_layer_forward / _backward): the
+    statistics pass (skipped when the convolution epilogue already wrote its partials), a tail kernel that finishes the
+    reduction, runs the SyncBN exchange over NVLink peer memory and finalises the statistics, and the apply pass.
+    The 16-bit copy of y travels in `box`; `aux` = (bn_a, bn_b, stat partials of x, of x2, peer exchange or None)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, x2, w2, b2, res, aux, relu, box):
+        bn_a, bn_b, sp_a, sp_b, ex = aux
+        L = cabi.lib()
+        x = x.contiguous()
+        n, C = x.shape
+        dev = x.device
+        fmt = _fmt16()
+        y = torch.empty_like(x)
+        y16 = torch.empty((n, C), dtype=_dtype16(fmt), device=dev) if fmt is not None else None
+        n_st = 4 * C + 2
+
+        def branch(xt, bn, sp, stats):
+            track = bn.track_running_stats and bn.running_mean is not None
+            sp_ptr, sp_rows = (sp.data_ptr(), sp.shape[0]) if sp is not None else (None, 0)
+            return cabi.BnBranch(xt.data_ptr(), sp_ptr, sp_rows, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                 bn.running_mean.data_ptr() if track else None,
+                                 bn.running_var.data_ptr() if track else None,
+                                 bn.num_batches_tracked.data_ptr() if track else None, bn.eps,
+                                 0.1 if bn.momentum is None else bn.momentum, stats.data_ptr())
+
+        if x2 is not None:
+            x2 = x2.contiguous()
+            stats = torch.empty((2, n_st), dtype=torch.float32, device=dev)
+            st_a, st_b = stats[0], stats[1]
+            br_b = C_byref(branch(x2, bn_b, sp_b, st_b))
+        else:
+            st_a, st_b, br_b = torch.empty(n_st, dtype=torch.float32, device=dev), None, None
+        if res is not None:
+            res = res.contiguous()
+        cabi.check(L.lg_bn_layer_forward(C_byref(branch(x, bn_a, sp_a, st_a)), br_b, cabi.ptr(res), 1 if relu else 0,
+                                         n, C, y.data_ptr(), cabi.ptr(y16), fmt if fmt is not None else 0,
+                                         cabi.peer_ctx(ex, 2 if x2 is not None else 1), cabi.stream_of(x)),
+                   "lg_bn_layer_forward")
+        if cabi.is_counting():
+            cabi.count_launches("lg_bn_layer_forward", 1 + (1 if sp_a is not None else 2) +
+                                (0 if x2 is None else (1 if sp_b is not None else 2)))
+        box["y16"], box["fmt"] = y16, fmt
+        ctx.save_for_backward(x, x2, y if relu else None, st_a, st_b, w, w2)
+        ctx.meta = (relu, res is not None, fmt, ex)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = cabi.lib()
+        x, x2, y, st_a, st_b, w, w2 = ctx.saved_tensors
+        relu, has_res, fmt, ex = ctx.meta
+        dy = dy.contiguous()
+        n, C = x.shape
+        dev = x.device
+        use16 = fmt is not None
+        d16 = _dtype16(fmt) if use16 else None
+        scales = torch.empty(12, dtype=torch.float32, device=dev)
+
+        def branch(xt, st, gamma):
+            dx = torch.empty_like(xt)
+            dx16 = torch.empty((n, C), dtype=d16, device=dev) if use16 else None
+            dgb = torch.empty((2, C), dtype=torch.float32, device=dev)
+            return dx, dx16, dgb, cabi.BnBwdBranch(xt.data_ptr(), st.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
+                                                   cabi.ptr(dx16), dgb.data_ptr(), dgb.data_ptr() + 4 * C)
+
+        dx, dx16, dgb, br_a = branch(x, st_a, w)
+        dx2 = dx2_16 = dgb2 = br_b = None
+        if x2 is not None:
+            dx2, dx2_16, dgb2, br_b = branch(x2, st_b, w2)
+            br_b = C_byref(br_b)
+        dres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[6]) else None
+        cabi.check(L.lg_bn_layer_backward(dy.data_ptr(), cabi.ptr(y), 1 if relu else 0, n, C, C_byref(br_a), br_b,
+                                          cabi.ptr(dres), fmt if use16 else 0, scales.data_ptr(),
+                                          cabi.peer_ctx(ex, 1), cabi.stream_of(x)), "lg_bn_layer_backward")
+        dw, db = dgb[0], dgb[1]
+        dw2 = db2 = None
+        if use16:
+            publish_grad16(dx, dx16, scales, fmt)
+        if x2 is not None:
+            dw2, db2 = dgb2[0], dgb2[1]
+            if use16:
+                publish_grad16(dx2, dx2_16, scales[4:], fmt)
+        return dx, dw, db, dx2, dw2, db2, dres, None, None, None
+
+
+class FusedBNFunctionFine(torch.autograd.Function):
+    """Fine-grained form of FusedBNFunction (5-9 library calls per layer each way): SyncBN over NCCL when the peer-memory
+    exchange is unavailable, and LIDOG_LAYER_CALLS=0 for A/B runs.  Same arithmetic, same kernels for the two passes."""
 
     @staticmethod
     def forward(ctx, x, w, b, x2, w2, b2, res, bn_a, bn_b, relu, box):
@@ -164,13 +257,9 @@ class FusedBNFunction(torch.autograd.Function):
             coef_b, scale_b, dw2, db2 = branch(1, st_b, w2, count_b, w2 is not None)
             dx2 = torch.empty_like(x2)
             dx2_16 = torch.empty(x2.shape, dtype=d16, device=dev) if use16 else None
-        dres = dres16 = scale_r = None
+        dres = dres16 = scale_r = None  # (no 16-bit copy of the residual gradient: no convolution consumes it)
         if has_res and ctx.needs_input_grad[6]:
             dres = torch.empty_like(x)
-            if use16:
-                dres16 = torch.empty(x.shape, dtype=d16, device=dev)
-                scale_r = torch.empty(4, dtype=torch.float32, device=dev)
-                cabi.check(L.lg_bn_bwd_gscale(cabi.ptr(maxes), C, cabi.ptr(scale_r), cabi.stream()), "lg_bn_bwd_gscale")
         cabi.check(L.lg_bn_bwd_apply(cabi.ptr(dy), cabi.ptr(y), cabi.ptr(x), cabi.ptr(st_a), cabi.ptr(coef_a),
                                      cabi.ptr(x2), cabi.ptr(st_b), cabi.ptr(coef_b), int(relu), n, C, cabi.ptr(dx),
                                      cabi.ptr(dx16), cabi.ptr(scale_a), cabi.ptr(dx2), cabi.ptr(dx2_16),
@@ -180,15 +269,24 @@ class FusedBNFunction(torch.autograd.Function):
             publish_grad16(dx, dx16, scale_a, fmt)
             if dx2 is not None:
                 publish_grad16(dx2, dx2_16, scale_b, fmt)
-            if dres is not None:
-                publish_grad16(dres, dres16, scale_r, fmt)
         return dx, dw, db, dx2, dw2, db2, dres, None, None, None, None
 
 
 def _fusable(bn, feats: torch.Tensor) -> bool:
+    """Decided from properties every rank of a SyncBN group shares (module configuration, dtype, channel count) --
+    never from the local row count: a rank whose scan leaves 0 or 1 voxels at some stride must still take part in
+    the same exchange as its peers (the kernels handle n = 0)."""
     return (CONFIG["fused"] and bn.training and feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 2
-            and feats.shape[0] > 1 and feats.shape[1] % 4 == 0 and feats.shape[1] <= 1024 and bn.affine
+            and feats.shape[1] % 4 == 0 and feats.shape[1] <= 1024 and bn.affine
             and (bn.momentum is not None or not bn.track_running_stats))
+
+
+def _partials_of(t: SparseTensor):
+    """Epilogue statistics of the convolution that produced `t` (me/conv.py), if they still describe t.F."""
+    sp = getattr(t, "_stat_partials", None)
+    if sp is None or sp[1] != t.F._version:
+        return None
+    return sp[0]
 
 
 class DeferredBN(SparseTensor):
@@ -222,7 +320,19 @@ class DeferredBN(SparseTensor):
         elif r is not None:
             res = r.F if isinstance(r, SparseTensor) else r
         box = {}
-        self._value = FusedBNFunction.apply(self._src.F, bn.weight, bn.bias, x2, w2, b2, res, bn, bn_b, bool(relu), box)
+        src = self._src
+        pg, _ = _group(bn)
+        ex = None
+        if pg is not None:
+            from . import peer
+            ex = peer.get(pg)
+        if CONFIG["layer_calls"] and (pg is None or ex is not None):
+            sp_a = _partials_of(src)
+            sp_b = _partials_of(r._src) if x2 is not None else None
+            self._value = FusedBNFunction.apply(src.F, bn.weight, bn.bias, x2, w2, b2, res, (bn, bn_b, sp_a, sp_b, ex),
+                                                bool(relu), box)
+        else:
+            self._value = FusedBNFunctionFine.apply(src.F, bn.weight, bn.bias, x2, w2, b2, res, bn, bn_b, bool(relu), box)
         if box.get("y16") is not None:  # the next convolution's operand: no separate cast pass
             f = self._value
             self._f16_cache = ((box["fmt"], f._version, f.data_ptr()), box["y16"])

@@ -22,7 +22,6 @@ _INSTANCES = {}
 
 class PeerExchange:
     def __init__(self, pg):
-        import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         L = cabi.lib()
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -30,8 +29,7 @@ class PeerExchange:
         self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, pg.group_name)
-        torch.cuda.synchronize()
-        dist.barrier(group=pg)  # every buffer is zeroed before anyone raises a flag
+        torch.cuda.synchronize()  # this rank's buffer is zeroed; `get` agrees with the peers before any flag is raised
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
         self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
         self.epoch = 0
@@ -46,14 +44,34 @@ class PeerExchange:
 
 
 def get(pg):
-    """The exchange of a process group, or None when disabled / unavailable (callers then use NCCL)."""
-    if not CONFIG["enabled"]:
-        return None
+    """The exchange of a process group, or None when disabled / unavailable (callers then use NCCL).
+
+    The choice is COLLECTIVE: every rank tries the set-up, then the ranks agree with an all-reduce(MIN) of their
+    success flags (which is also the barrier after which every buffer is known to be zeroed).  A rank whose
+    rendezvous failed can therefore never leave its peers spinning on a flag it will not raise."""
     key = id(pg)
     if key not in _INSTANCES:
-        try:
-            _INSTANCES[key] = PeerExchange(pg)
-        except Exception as e:  # no symmetric memory on this system: NCCL carries the exchange
-            warnings.warn(f"lidog_b200: peer-memory SyncBN exchange unavailable ({e!r}); using NCCL all_reduce")
-            _INSTANCES[key] = None
+        import torch.distributed as dist
+        ex, why = None, "disabled (LIDOG_PEER_SYNCBN=0)"
+        if CONFIG["enabled"]:
+            try:
+                ex = PeerExchange(pg)
+            except Exception as e:  # no symmetric memory on this system
+                why = repr(e)
+        ok = torch.tensor([1 if ex is not None else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
+        if int(ok.item()) == 0:
+            if CONFIG["enabled"]:
+                warnings.warn(f"lidog_b200: peer-memory SyncBN exchange unavailable on at least one rank ({why}); "
+                              f"using NCCL all_reduce")
+            ex = None
+        _INSTANCES[key] = ex
     return _INSTANCES[key]
+
+
+def active(pg=None) -> bool:
+    """Whether the peer-memory exchange (not NCCL) carries SyncBN for `pg` -- what bench.py reports."""
+    if pg is None:
+        import torch.distributed as dist
+        pg = dist.group.WORLD
+    return _INSTANCES.get(id(pg)) is not None

@@ -16,6 +16,8 @@ from .coords import CoordinateManager
 
 
 class SparseTensor:
+    _stat_partials = None  # (per-tile column statistics written by the producing convolution's epilogue, F version)
+
     def __init__(self, features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
                  coordinate_manager=None, quantization_mode=None, device=None, **unused):
         if not isinstance(features, torch.Tensor):
@@ -91,7 +93,7 @@ class SparseTensor:
             src = f.detach().contiguous()
             out = torch.empty(src.shape, dtype=torch.float16 if fmt == cabi.FMT_FP16 else torch.bfloat16,
                               device=src.device)
-            cabi.check(cabi.lib().lg_cast_rows(cabi.ptr(src), cabi.ptr(out), src.numel(), fmt, None, cabi.stream()),
+            cabi.check(cabi.lib().lg_cast_rows(cabi.ptr(src), cabi.ptr(out), src.numel(), fmt, None, cabi.stream_of(src)),
                        "lg_cast_rows")
             self._f16_cache = (key, out)
         return self._f16_cache[1]

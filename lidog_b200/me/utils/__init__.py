@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from ... import cabi
-from ..coords import coords_unique
+from ..coords import build_levels, coords_unique
 
 
 def _device(device=None):
@@ -39,7 +39,7 @@ def quantize_points(points: torch.Tensor, quantization_size, batch_of_row: torch
         batch_of_row = batch_of_row.to(device=pts.device, dtype=torch.int32).contiguous()
     L = cabi.lib()
     fn, name = (L.lg_quantize_points_f64, "lg_quantize_points_f64") if f64 else (L.lg_quantize_points, "lg_quantize_points")
-    cabi.check(fn(cabi.ptr(pts), cabi.ptr(batch_of_row), pts.shape[0], sx, sy, sz, cabi.ptr(out), cabi.stream()), name)
+    cabi.check(fn(cabi.ptr(pts), cabi.ptr(batch_of_row), pts.shape[0], sx, sy, sz, cabi.ptr(out), cabi.stream_of(pts)), name)
     return out
 
 
@@ -102,7 +102,8 @@ def sparse_quantize_batch(points_list, labels_list, quantization_size, ignore_la
     """Voxelise a whole batch of device point clouds with one hash build.
 
     -> dict(coords int32 [U,4] (batch first), unique_map int64 [U] into the concatenated points,
-            inverse_map int64 [N], colabels int32 [U], counts per scan (host list))."""
+            inverse_map int64 [N], colabels int32 [U], levels = every coordinate level of the batch
+            (`CoordinateManager.from_quantized` adopts them: one hashed voxel index for voxelisation and network))."""
     dev = points_list[0].device
     sizes = [p.shape[0] for p in points_list]
     pts = torch.cat(points_list, 0)
@@ -111,7 +112,9 @@ def sparse_quantize_batch(points_list, labels_list, quantization_size, ignore_la
     b = torch.cat([torch.full((n,), i, dtype=torch.int32, device=dev) for i, n in enumerate(sizes)], 0)
     q4 = quantize_points(pts, quantization_size, b)
     lab = None if labels_list is None else torch.cat(labels_list, 0)
-    res = coords_unique(q4, 1, labels=lab, ignore_label=ignore_label)
+    levels = build_levels(q4, labels=lab, ignore_label=ignore_label)  # stride 1 + the encoder's strides, one sync
+    res = dict(levels[0])
+    res["levels"] = levels
     return res
 
 

@@ -25,3 +25,17 @@ def random_voxels(rng, n, span=40, batch=2):
     c = c[np.sort(first)]
     # batch-sorted like a collated batch
     return c[np.argsort(c[:, 0], kind="stable")]
+
+
+def record(name, **values):
+    """Append the measured numbers of a parity test to gpurun_out/r02_parity_measured.jsonl (the table in
+    profiles/ and the bars in the tests come from these lines, not from guesses)."""
+    import json
+    import os
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "r02_parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **values)) + "\n")
+    except OSError:
+        pass

@@ -26,9 +26,19 @@ def _sparse(cuda, n):
     return ME, base.coordinate_manager, coords.shape[0]
 
 
+@pytest.fixture(params=[1, 0], ids=["layer_calls", "fine_calls"])
+def layer_calls(request):
+    """Both host paths: one library call per layer each way (default) and the fine-grained entry points."""
+    from lidog_b200.me import norm, conv
+    old = norm.CONFIG["layer_calls"], conv.CONFIG["layer_calls"]
+    norm.CONFIG["layer_calls"] = conv.CONFIG["layer_calls"] = request.param
+    yield request.param
+    norm.CONFIG["layer_calls"], conv.CONFIG["layer_calls"] = old
+
+
 @pytest.mark.parametrize("C", [32, 96, 256])
 @pytest.mark.parametrize("mode", ["bn_relu", "bn", "bn_res_relu", "bn_bn_relu"])
-def test_fused_bn_matches_torch(cuda, C, mode):
+def test_fused_bn_matches_torch(cuda, C, mode, layer_calls):
     ME, cm, n = _sparse(cuda, 5000)
     torch.manual_seed(C)
     x = (torch.randn(n, C, device=cuda) * 2 + 0.5).requires_grad_(True)
@@ -84,7 +94,7 @@ def test_fused_bn_matches_torch(cuda, C, mode):
     assert y16.dtype == torch.float16 and torch.equal(y16, y_f.clamp(-65504, 65504).half())
 
 
-def test_fused_bn_hands_scaled_fp16_gradient_to_the_convolution(cuda):
+def test_fused_bn_hands_scaled_fp16_gradient_to_the_convolution(cuda, layer_calls):
     """conv -> BN -> ReLU: the BN backward publishes dx as a scaled fp16 copy; the convolution's backward uses it
     and the result equals the unfused path within the tensor-core tolerance."""
     ME, cm, n = _sparse(cuda, 6000)
@@ -108,6 +118,38 @@ def test_fused_bn_hands_scaled_fp16_gradient_to_the_convolution(cuda):
             norm.CONFIG["fused"] = 1
     for a, b in zip(outs[0], outs[1]):
         assert rel(a, b) <= 1e-3
+
+
+@pytest.mark.parametrize("C", [32, 96, 256])
+def test_epilogue_statistics_feed_the_batch_norm(cuda, C):
+    """conv -> BN -> ReLU with the statistics taken from the GEMM epilogue (LIDOG_EPI_STATS=1, the default) equals
+    the same chain with the separate statistics pass (=0): outputs, every gradient, running statistics."""
+    ME, cm, n = _sparse(cuda, 7000)
+    from lidog_b200.me import conv as meconv
+    torch.manual_seed(1)
+    conv = ME.MinkowskiConvolution(64, C, kernel_size=3, dimension=3).to(cuda)
+    x0 = torch.randn(n, 64, device=cuda).relu_()
+    gy = torch.randn(n, C, device=cuda) * 1e-3
+    outs = []
+    old = meconv.CONFIG["epi_stats"]
+    try:
+        for epi in (1, 0):
+            meconv.CONFIG["epi_stats"] = epi
+            bn = ME.MinkowskiBatchNorm(C).to(cuda)
+            x = x0.clone().requires_grad_(True)
+            conv.kernel.grad = None
+            c = conv(ME.SparseTensor(x, coordinate_manager=cm))
+            assert (c._stat_partials is not None) == bool(epi)
+            y = ME.MinkowskiReLU()(bn(c)).F
+            y.backward(gy)
+            outs.append((y.detach(), x.grad.clone(), conv.kernel.grad.clone(), bn.bn.weight.grad.clone(),
+                         bn.bn.bias.grad.clone(), bn.bn.running_mean.clone(), bn.bn.running_var.clone()))
+    finally:
+        meconv.CONFIG["epi_stats"] = old
+    # (the two convolution gradients pass through the fp16 rounding of the BN's dx: a 1e-7 change of a value flips
+    # the rounding of a few elements, which is worth ~1e-5 in the Frobenius norm)
+    for (a, b), tol in zip(zip(outs[0], outs[1]), (1e-5, 1e-4, 1e-4, 1e-5, 1e-5, 1e-5, 1e-5)):
+        assert rel(a, b) <= tol
 
 
 def test_fused_bn_eval_mode_uses_running_statistics(cuda):

@@ -5,6 +5,8 @@ import torch
 
 from oracle import voxel as ov
 
+from tests.helpers import record
+
 pytestmark = pytest.mark.gpu
 
 
@@ -59,6 +61,16 @@ def test_model_forward_backward_matches_oracle(cuda, mode, tol):
     def rel(a, b):
         return float((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm().clamp_min(1e-30))
 
+    per_layer = {}
+    ref_grads0 = dict(ref_model.named_parameters())
+    for name, p in model.named_parameters():
+        go = ref_grads0[name].grad
+        if p.grad is not None and go is not None and float(go.norm()) > 1e-12:
+            per_layer[name] = rel(p.grad, go)
+    record("model_forward_backward", mode=mode, voxels=int(len(q)), logits=rel(out.F, out_o.F),
+           bev=rel(bev["block8"], bev_o["block8"]), loss=abs(float(loss) - float(loss_o)),
+           grad_worst=max(per_layer.values()), grad_median=float(np.median(list(per_layer.values()))),
+           grad_worst_layer=max(per_layer, key=per_layer.get), per_layer=per_layer)
     assert rel(out.F, out_o.F) <= tol
     assert rel(bev["block8"], bev_o["block8"]) <= tol
     assert abs(float(loss) - float(loss_o)) <= tol * max(1.0, abs(float(loss_o)))

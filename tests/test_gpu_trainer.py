@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.helpers import record
+
 pytestmark = pytest.mark.gpu
 
 
@@ -82,6 +84,13 @@ def test_training_step_matches_oracle(cuda, mode, tol):
     ref_params = dict(ref_net.named_parameters())
     top = max(float(p.grad.norm()) for p in ref_params.values())
     bad = []
+    measured = {}
+    for name, p in net.named_parameters():
+        if p.grad is not None and float(ref_params[name].grad.norm()) > 1e-6 * top:
+            measured[name] = rel(p.grad, ref_params[name].grad)
+    record("training_step", mode=mode, loss_3d=abs(float(l3) - float(l3_o)), loss_bev=abs(float(l2) - float(l2_o)),
+           loss_total=abs(float(tot) - float(tot_o)), grad_worst=max(measured.values()),
+           grad_median=float(np.median(list(measured.values()))), grad_worst_layer=max(measured, key=measured.get))
     for name, p in net.named_parameters():
         g, go = p.grad, ref_params[name].grad
         assert g is not None and go is not None and torch.isfinite(g).all(), name

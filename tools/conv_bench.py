@@ -49,7 +49,7 @@ def main():
     ap.add_argument("--fmt", default="fp16")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cases", default="all")
-    ap.add_argument("--gather", default="0,2")
+    ap.add_argument("--gather", default="2")
     ap.add_argument("--only", default="fwd,dgrad,wgrad")
     ap.add_argument("--sorted", default="0,1", help="gather-plan row order: 0 natural, 1 mask-sorted")
     ap.add_argument("--points", type=int, default=0,

@@ -1,0 +1,41 @@
+#!/bin/bash
+# One parameterised GPU session script (replaces the per-session one-offs of round 1):
+#   gpurun --timeout 1500 -- 'bash tools/gpu_run.sh <tag> <step> [<step> ...]'
+# steps: tests | smoke | bench | bench_ab | host | micro | layers | launches | ncu_gemm | ncu_wgrad | ncu_hbm | sanitize |
+#        bench_cfg0 | bench_nuscenes | bench_mix3d | empty_cache
+# Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
+tag=$1; shift
+mkdir -p gpurun_out
+O=gpurun_out/${tag}
+for step in "$@"; do
+  echo "=== $step" | tee -a ${O}_steps.log
+  case $step in
+    tests)    timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee ${O}_gpu_tests.log ;;
+    tests_all) timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 2>&1 | tail -60 | tee ${O}_gpu_tests.log ;;
+    smoke)    timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee ${O}_smoke.log ;;
+    bench)    timeout 900 python bench.py --steps 8 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
+    bench_nocpu) timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
+    bench_ab) for cfg in "LIDOG_LAYER_CALLS=0" "LIDOG_EPI_STATS=0"; do
+                env $cfg timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > ${O}_bench_${cfg}.json 2> ${O}_bench_${cfg}.err
+                tail -1 ${O}_bench_${cfg}.err | cut -c1-300; done ;;
+    empty_cache) timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --empty-cache > ${O}_bench_empty_cache.json 2> ${O}_bench_empty_cache.err; tail -1 ${O}_bench_empty_cache.err | cut -c1-300 ;;
+    bench_cfg0) timeout 900 python bench.py --steps 8 --warmup 3 --batch 1 --classes 19 > ${O}_bench_cfg0.json 2> ${O}_bench_cfg0.err; tail -1 ${O}_bench_cfg0.err | cut -c1-300 ;;
+    bench_nuscenes) timeout 600 python bench.py --steps 8 --warmup 3 --shape nuscenes --batch 16 --no-cpu-baseline > ${O}_bench_nuscenes.json 2> ${O}_bench_nuscenes.err; tail -1 ${O}_bench_nuscenes.err | cut -c1-300 ;;
+    bench_mix3d) timeout 600 python bench.py --steps 8 --warmup 3 --shape mix3d --batch 8 --no-cpu-baseline > ${O}_bench_mix3d.json 2> ${O}_bench_mix3d.err; tail -1 ${O}_bench_mix3d.err | cut -c1-300 ;;
+    host)     timeout 300 python tools/host_profile.py > ${O}_host_profile.txt 2>&1; head -3 ${O}_host_profile.txt ;;
+    micro)    timeout 900 python tools/microbench.py > ${O}_microbench.jsonl 2> ${O}_microbench.err; tail -3 ${O}_microbench.jsonl | cut -c1-300 ;;
+    layers)   timeout 300 python tools/layer_table.py > ${O}_layer_table.txt 2> ${O}_layer_table.err; head -3 ${O}_layer_table.txt | cut -c1-300 ;;
+    convnet)  timeout 300 python tools/conv_bench.py --cases net --sorted 1 --reps 10 > ${O}_conv_net.txt 2>&1; tail -30 ${O}_conv_net.txt | cut -c1-200 ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+                --log-file ${O}_launches.csv python bench.py --ncu > ${O}_ncu1.log 2>&1
+              python tools/launch_summary.py ${O}_launches.csv > ${O}_launch_summary.txt 2>&1; head -45 ${O}_launch_summary.txt ;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm2 -s 60 -c 2 \
+                -o ${O}_ncu_gemm2 -f python bench.py --ncu > ${O}_ncu2.log 2>&1; ls -la ${O}_ncu_gemm2.ncu-rep ;;
+    ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_wgrad -s 2 -c 2 \
+                -o ${O}_ncu_wgrad2 -f python bench.py --ncu > ${O}_ncu3.log 2>&1; ls -la ${O}_ncu_wgrad2.ncu-rep ;;
+    ncu_hbm)  timeout 900 ncu --set full --clock-control none --profile-from-start off \
+                -k regex:'k_bn_|k_neighbors|k_bev_|k_insert|k_conv_c1' -c 60 -o ${O}_ncu_hbm -f python bench.py --ncu > ${O}_ncu4.log 2>&1; ls -la ${O}_ncu_hbm.ncu-rep ;;
+    sanitize) bash tools/sanitize.sh ${O} ;;
+    *) echo "unknown step $step" ;;
+  esac
+done

@@ -33,29 +33,47 @@ def main():
     x = torch.randn(n, C, device=dev) * (1 + rank) + 0.3
     res = torch.randn(n, C, device=dev)
     gy = torch.randn(n, C, device=dev) * 1e-3
-    worst = 0.0
-    out = {}
-    for fused in (1, 0):
-        norm.CONFIG["fused"] = fused
+    from lidog_b200.me import peer
+    x2 = torch.randn(n, C, device=dev) - 0.5 * rank
+
+    def run(fused, layer_calls, two_branches):
+        norm.CONFIG["fused"], norm.CONFIG["layer_calls"] = fused, layer_calls
         dt = torch.float32 if fused else torch.float64
-        m = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(ME.MinkowskiBatchNorm(C)).to(dev).to(dt)
-        with torch.no_grad():
-            g = torch.Generator(device="cpu").manual_seed(1)
-            m.bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
-            m.bn.bias.copy_(torch.randn(C, generator=g) * 0.1)
-        xs, rs = x.detach().clone().to(dt).requires_grad_(True), res.detach().clone().to(dt).requires_grad_(True)
-        o = m(ME.SparseTensor(xs, coordinate_manager=cm))
-        o += ME.SparseTensor(rs, coordinate_manager=cm)
+        ms = []
+        for s in (1, 2):
+            m = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(ME.MinkowskiBatchNorm(C)).to(dev).to(dt)
+            with torch.no_grad():
+                g = torch.Generator(device="cpu").manual_seed(s)
+                m.bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+                m.bn.bias.copy_(torch.randn(C, generator=g) * 0.1)
+            ms.append(m)
+        xs, rs, x2s = (t.detach().clone().to(dt).requires_grad_(True) for t in (x, res, x2))
+        o = ms[0](ME.SparseTensor(xs, coordinate_manager=cm))
+        if two_branches:  # BasicBlock with a downsample branch: BN_a(x) + BN_b(x2)
+            o += ms[1](ME.SparseTensor(x2s, coordinate_manager=cm))
+        else:
+            o += ME.SparseTensor(rs, coordinate_manager=cm)
         y = ME.MinkowskiReLU()(o).F
         y.backward(gy.to(dt))
-        out[fused] = [y.detach(), xs.grad, rs.grad, m.bn.weight.grad, m.bn.bias.grad, m.bn.running_mean, m.bn.running_var]
-    names = ["y", "dx", "dres", "dgamma", "dbeta", "running_mean", "running_var"]
-    errs = {k: rel(a, b) for k, a, b in zip(names, out[1], out[0])}
-    worst = max(errs.values())
+        second = [x2s.grad, ms[1].bn.weight.grad, ms[1].bn.running_var] if two_branches else [rs.grad]
+        return [y.detach(), xs.grad, ms[0].bn.weight.grad, ms[0].bn.bias.grad, ms[0].bn.running_mean,
+                ms[0].bn.running_var] + second
+
+    worst = 0.0
+    report = {}
+    for two in (False, True):
+        ref = run(0, 1, two)
+        for lc in (1, 0):  # one library call per layer with the in-kernel exchange / fine-grained calls + lg_peer_sum
+            got = run(1, lc, two)
+            errs = [rel(a, b) for a, b in zip(got, ref)]
+            report[f"two_branches={two},layer_calls={lc}"] = f"{max(errs):.2e}"
+            worst = max(worst, max(errs))
+    norm.CONFIG["fused"], norm.CONFIG["layer_calls"] = 1, 1
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("syncbn fused vs torch SyncBatchNorm(f64):", {k: f"{v:.2e}" for k, v in errs.items()}, "worst over ranks", float(t))
+        print("syncbn fused vs torch SyncBatchNorm(f64), world", dist.get_world_size(), "exchange:",
+              "peer memory (in-kernel)" if peer.active() else "NCCL", report, "worst over ranks", float(t))
         assert float(t) <= 1e-5, float(t)
         print("SYNCBN OK")
     dist.destroy_process_group()
