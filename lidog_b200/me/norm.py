@@ -114,7 +114,7 @@ class FusedBNFunction(torch.autograd.Function):
         fmt = _fmt16()
         y = torch.empty_like(x)
         y16 = torch.empty((n, C), dtype=_dtype16(fmt), device=dev) if fmt is not None else None
-        n_st = 4 * C + 2
+        n_st = 4 * C + 4  # [4C + 2] used; rows of the two-branch tensor must stay 16-byte aligned (float4 reads)
 
         def branch(xt, bn, sp, stats):
             track = bn.track_running_stats and bn.running_mean is not None
