@@ -211,6 +211,7 @@ def run_ours(args):
     from lidog_b200.me import conv as meconv
     from lidog_b200.me import norm as menorm
     from lidog_b200.me import peer as mepeer
+    from lidog_b200.me import coords as mecoords
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,12 +257,14 @@ def run_ours(args):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mecoords.SYNC_WAIT.update(seconds=0.0, count=0)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        host["issue_ms"] = 1e3 * (time.perf_counter() - t0) / steps  # host time to ISSUE a step (no sync inside)
+        host["issue_ms"] = 1e3 * (time.perf_counter() - t0) / steps  # wall time of the host loop, waits included
+        host["wait_ms"] = 1e3 * mecoords.SYNC_WAIT["seconds"] / steps  # of which: blocked in the step's one sync
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -294,7 +297,7 @@ def run_ours(args):
     # ---- headline: the UNINSTRUMENTED loop (no per-launch events, no call counting)
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms = timed(resident_step, args.steps)
-    host_issue_ms = host.get("issue_ms")
+    host_issue_ms, host_wait_ms = host.get("issue_ms"), host.get("wait_ms")
     clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * args.batch / (ms_per_step / 1e3)
@@ -384,7 +387,11 @@ def run_ours(args):
                            "bev_layout": "channels_last" if lbev.CONFIG["channels_last"] else "nchw"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "sparse_conv_ms_per_scan": conv_ms / args.batch, "kernels": kernels,
-                "host_issue_ms_per_step": host_issue_ms,
+                "host_issue_ms_per_step": host_issue_ms, "host_wait_ms_per_step": host_wait_ms,
+                "host_busy_ms_per_step": None if host_issue_ms is None else host_issue_ms - host_wait_ms,
+                "host_note": "issue = wall time of the Python loop for one step; wait = the part spent blocked in the "
+                             "step's single synchronisation (coordinate-level counts, waiting for the GPU to drain the "
+                             "previous step); busy = issue - wait = the CPU work of launching a step",
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -10,6 +10,7 @@ arithmetic happens in liblidog_b200 (csrc/coords.cu, csrc/kmap.cu).
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import torch
 
@@ -57,6 +58,7 @@ def coords_unique(coords: torch.Tensor, stride: int = 1, labels: torch.Tensor | 
 # Anything else is still derived on demand by `CoordinateManager.level` (one host round trip each).
 PREBUILD_STRIDES = (2, 4, 8, 16)
 _PINNED = {}
+SYNC_WAIT = {"seconds": 0.0, "count": 0}  # host time blocked in the coordinate pyramid's synchronisation (bench.py)
 
 
 def build_levels(coords: torch.Tensor, labels: torch.Tensor | None = None, ignore_label: int = -100,
@@ -97,7 +99,10 @@ def build_levels(coords: torch.Tensor, labels: torch.Tensor | None = None, ignor
                                    (C.c_int32 * nl)(*strides), outs, counts.data_ptr(), host.data_ptr(), stream),
                "lg_coords_pyramid")
     cabi.count_launches("lg_coords_pyramid", 7 * nl + (1 if labels is not None else 0))
+    t0 = time.perf_counter()
     torch.cuda.current_stream(dev).synchronize()  # the one host round trip of the step's coordinate work
+    SYNC_WAIT["seconds"] += time.perf_counter() - t0
+    SYNC_WAIT["count"] += 1
     cs = host.tolist()
     res, n_in = [], n
     for l in range(nl):

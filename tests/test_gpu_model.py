@@ -26,8 +26,19 @@ def _build(ME, bev_fn, state=None, bound=12.0):
     return m
 
 
+@pytest.fixture(params=[False, True], ids=["head_fp32", "head_tf32"])
+def head_tf32(request):
+    """The dense 2D head stays in cuDNN (north_star) and PyTorch runs cuDNN convolutions in TF32 by default -- the
+    precision the reference itself trains its head in.  `head_fp32` switches that off so the measured error is the
+    sparse path's own; `head_tf32` is the configuration the bench (and the reference) run."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = request.param
+    yield request.param
+    torch.backends.cudnn.allow_tf32 = old
+
+
 @pytest.mark.parametrize("mode,tol", [("off", 2e-3), ("fp16", 3e-2)])
-def test_model_forward_backward_matches_oracle(cuda, mode, tol):
+def test_model_forward_backward_matches_oracle(cuda, mode, tol, head_tf32):
     import MinkowskiEngine as ME
     from lidog_b200.me import conv as meconv
     from lidog_b200.lidog.bev import sparse2super
@@ -67,7 +78,7 @@ def test_model_forward_backward_matches_oracle(cuda, mode, tol):
         go = ref_grads0[name].grad
         if p.grad is not None and go is not None and float(go.norm()) > 1e-12:
             per_layer[name] = rel(p.grad, go)
-    record("model_forward_backward", mode=mode, voxels=int(len(q)), logits=rel(out.F, out_o.F),
+    record("model_forward_backward", mode=mode, head_tf32=head_tf32, voxels=int(len(q)), logits=rel(out.F, out_o.F),
            bev=rel(bev["block8"], bev_o["block8"]), loss=abs(float(loss) - float(loss_o)),
            grad_worst=max(per_layer.values()), grad_median=float(np.median(list(per_layer.values()))),
            grad_worst_layer=max(per_layer, key=per_layer.get), per_layer=per_layer)

@@ -33,8 +33,19 @@ def _batch():
     return [a, np.concatenate(parts)], [la, np.concatenate(labs).astype(np.int32)]
 
 
+@pytest.fixture(params=[False, True], ids=["head_fp32", "head_tf32"])
+def head_tf32(request):
+    """The dense 2D head stays in cuDNN (north_star) and PyTorch runs cuDNN convolutions in TF32 by default -- the
+    precision the reference itself trains its head in.  `head_fp32` switches that off so the measured error is the
+    sparse path's own; `head_tf32` is the configuration the bench (and the reference) run."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = request.param
+    yield request.param
+    torch.backends.cudnn.allow_tf32 = old
+
+
 @pytest.mark.parametrize("mode,tol", [("off", 2e-3), ("fp16", 3e-2)])
-def test_training_step_matches_oracle(cuda, mode, tol):
+def test_training_step_matches_oracle(cuda, mode, tol, head_tf32):
     import MinkowskiEngine as ME
     from lidog_b200.me import conv as meconv
     from lidog_b200.lidog import model as M, step
@@ -88,7 +99,7 @@ def test_training_step_matches_oracle(cuda, mode, tol):
     for name, p in net.named_parameters():
         if p.grad is not None and float(ref_params[name].grad.norm()) > 1e-6 * top:
             measured[name] = rel(p.grad, ref_params[name].grad)
-    record("training_step", mode=mode, loss_3d=abs(float(l3) - float(l3_o)), loss_bev=abs(float(l2) - float(l2_o)),
+    record("training_step", mode=mode, head_tf32=head_tf32, loss_3d=abs(float(l3) - float(l3_o)), loss_bev=abs(float(l2) - float(l2_o)),
            loss_total=abs(float(tot) - float(tot_o)), grad_worst=max(measured.values()),
            grad_median=float(np.median(list(measured.values()))), grad_worst_layer=max(measured, key=measured.get))
     for name, p in net.named_parameters():

@@ -132,3 +132,87 @@ def test_reference_bev_label_image_equals_the_device_function(relpath):
         assert ref_img.shape == (img, img)
         assert np.array_equal(ref_img.astype(np.int64), got[0].numpy()), (seed, bound)
         assert (ref_img >= 0).sum() > 50
+
+
+def _reference_items(scans, me, Conv, bound, img, voxel=0.05):
+    """The per-scan dictionaries the reference dataset's __getitem__ builds (semantickitti_bev.py:209-290), from the
+    same calls: the shim's sparse_quantize, the reference's own PC2ImgConverter."""
+    bounds = [[-bound, bound], [-bound, bound], [-10, 8]]
+    conv = Conv(imgChannel=1, xRange=bounds[0], yRange=bounds[1], zRange=bounds[2], xGridSize=2 * bound / img,
+                yGridSize=2 * bound / img, zGridSize=0.3)
+    items = []
+    for i, (pts, lab) in enumerate(scans):
+        colors = np.ones((len(pts), 1), np.float32)                                         # :194
+        q, _, qlab, vidx, inv = me.utils.sparse_quantize(pts, colors, labels=lab, ignore_label=-1,
+                                                         quantization_size=voxel, return_index=True,
+                                                         return_inverse=True)               # :232-238
+        bev_points = (np.asarray(q) * voxel).astype(np.float32)                              # :244
+        bl, bs = conv.getBEVImageNew(bev_points, np.asarray(qlab))                           # :249
+        items.append({"coordinates": torch.as_tensor(np.asarray(q)), "features": torch.from_numpy(colors[np.asarray(vidx)]),
+                      "sem_labels": torch.from_numpy(lab[np.asarray(vidx)]), "xyz": torch.from_numpy(pts[np.asarray(vidx)]),
+                      "idx": torch.tensor(i), "sampled_idx": torch.as_tensor(np.asarray(vidx)),
+                      "bev_labels": {"block8": torch.from_numpy(bl).long()},
+                      "bev_selected_idx": {"block8": torch.from_numpy(bs).long()}})
+    return items
+
+
+def test_reference_collation_and_training_step_run_unchanged_and_equal_the_mirror():
+    """collation.py:274-325 + trainer_lighting_2d.py:141-293,349-360 with the LiDOG configuration
+    (configs/lidog/single/semantickitti.yaml: SoftDICELoss + DICELoss, weights 0.5/0.5, Adam 1e-3, warmup 0,
+    clear_cache_int 1) against LidogTrainer: same batch products, same losses, same gradients, same Adam step."""
+    from oracle import me_cpu
+    from oracle.me_cpu.bevfn import sparse2super as o_s2s
+    from lidog_b200.lidog import model as M, step
+    bound, img = 8.0, 27  # 2 * 8 m / 0.05 = 320 px -> MaxPool2d(5,3,1) 106 -> two stride-2 convs -> 27 (kitti: 2000 -> 167)
+    scans = [_scan(21, bound), _scan(22, bound)]
+    Conv = _reference_class("utils/datasets/semantickitti_bev.py", "PC2ImgConverter")
+    with rh.reference(me_cpu):
+        import utils.collation.collation as coll
+        import utils.models.minkunet_bev as ref
+        tr2d = rh.load_file("utils/pipelines/trainer_lighting_2d.py", "trainer_lighting_2d")
+        batch = coll.CollateFNSingleSourceBEVMultiLevel(device=None)(_reference_items(scans, me_cpu, Conv, bound, img))
+        assert batch["source_coordinates0"].dtype == torch.float32 and batch["source_coordinates0"].shape[1] == 4
+        torch.manual_seed(0)
+        net_r = ref.MinkUNet34BEV(1, 7, 3, mapping_bound_2d=bound)
+        state = {k: v.clone() for k, v in net_r.state_dict().items()}
+        ds = rh.FakeDataset(7)
+        plt = tr2d.PLTTrainer2D(model=net_r, training_dataset=ds, validation_dataset=ds, optimizer_name="Adam",
+                                sem_criterion="SoftDICELoss", sem_bev_criterion="DICELoss", aux_criterion=None,
+                                warmup_epochs=0, lr=1e-3, batch_size=2, weight_decay=1e-4, num_classes=7, clear_cache_int=1,
+                                source_weights=[0.5, 0.5], source_domains_name=["SemanticKITTI-BEV"],
+                                target_domains_name=None)
+        opt = plt.configure_optimizers()
+        plt.trainer.optimizers = [opt]
+        torch.set_num_threads(1)  # deterministic index_put_ in the reference's sparse2super
+        opt.zero_grad()
+        total_r = plt.training_step(batch, 0)  # the UNCHANGED step: builds ME.SparseTensor, model, CPU losses, metrics
+        total_r.backward()
+        grads_r = {k: p.grad.clone() for k, p in net_r.named_parameters()}
+        opt.step()
+        logged = dict(plt.logged)
+
+    # the mirror on the same scans: device-style batched voxelisation + label products, same weights
+    net_m = M.MinkUNet34BEV(1, 7, ME=me_cpu, bev_fn=o_s2s, mapping_bound_2d=bound)
+    net_m.load_state_dict(state)
+    mir = step.LidogTrainer(net_m, num_classes=7, shape="nuscenes", ME=me_cpu)
+    mir.bound, mir.bev_img = bound, img
+    P, Lb = [torch.from_numpy(p) for p, _ in scans], [torch.from_numpy(l) for _, l in scans]
+    coords, feats, sem, bev, cm = mir.voxelize(P, Lb)
+    assert torch.equal(coords.to(torch.float32), batch["source_coordinates0"])            # batched voxel coordinates
+    assert torch.equal(sem, batch["source_sem_labels0"].long())                            # first-point labels
+    assert torch.equal(bev, batch["source_bev_labels0"]["block8"])                         # BEV label images
+    total_m, l3, l2 = mir.forward_loss(coords, feats, sem, bev, len(P), cm)
+    mir.optimizer.zero_grad(set_to_none=True)
+    total_m.backward()
+    assert abs(float(total_m) - float(total_r)) <= 1e-6, (float(total_m), float(total_r))
+    key3d = "training/SemanticKITTI-BEV/sem_loss0"
+    assert abs(logged[key3d] - float(l3)) <= 1e-6 and abs(logged["training/SemanticKITTI-BEV/bev_loss0"] - float(l2)) <= 1e-6
+    worst = 0.0
+    for k, p in net_m.named_parameters():
+        g, gr = p.grad, grads_r[k]
+        if float(gr.norm()) > 1e-10:
+            worst = max(worst, float((g - gr).norm() / gr.norm()))
+    assert worst <= 1e-4, worst  # same arithmetic; masked-sum losses instead of boolean indexing reorder float sums
+    mir.optimizer.step()
+    moved = max(float((p.detach() - net_r.state_dict()[k]).abs().max()) for k, p in net_m.named_parameters())
+    assert moved <= 5e-4, moved  # both took the same Adam(lr 1e-3, wd 1e-4) step (|update| ~ 1e-3 each)

@@ -12,6 +12,7 @@ for step in "$@"; do
   case $step in
     tests)    timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee ${O}_gpu_tests.log ;;
     tests_all) timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 2>&1 | tail -60 | tee ${O}_gpu_tests.log ;;
+    tests_e2e) timeout 900 python -m pytest tests/test_gpu_fullscale.py tests/test_gpu_model.py tests/test_gpu_trainer.py -m gpu -q 2>&1 | tail -15 | tee ${O}_gpu_tests_e2e.log ;;
     smoke)    timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee ${O}_smoke.log ;;
     bench)    timeout 900 python bench.py --steps 8 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
     bench_nocpu) timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
@@ -29,9 +30,9 @@ for step in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
                 --log-file ${O}_launches.csv python bench.py --ncu > ${O}_ncu1.log 2>&1
               python tools/launch_summary.py ${O}_launches.csv > ${O}_launch_summary.txt 2>&1; head -45 ${O}_launch_summary.txt ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm2 -s 60 -c 2 \
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm2 -s 58 -c 2 \
                 -o ${O}_ncu_gemm2 -f python bench.py --ncu > ${O}_ncu2.log 2>&1; ls -la ${O}_ncu_gemm2.ncu-rep ;;
-    ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_wgrad -s 2 -c 2 \
+    ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_wgrad -s 0 -c 2 \
                 -o ${O}_ncu_wgrad2 -f python bench.py --ncu > ${O}_ncu3.log 2>&1; ls -la ${O}_ncu_wgrad2.ncu-rep ;;
     ncu_hbm)  timeout 900 ncu --set full --clock-control none --profile-from-start off \
                 -k regex:'k_bn_|k_neighbors|k_bev_|k_insert|k_conv_c1' -c 60 -o ${O}_ncu_hbm -f python bench.py --ncu > ${O}_ncu4.log 2>&1; ls -la ${O}_ncu_hbm.ncu-rep ;;
