@@ -54,31 +54,30 @@ def main():
         bl, _ = conv.getBEVImageNew((q * 0.05).astype(np.float32), colab)
         out[f"bev_{tag}_coords"], out[f"bev_{tag}_colabels"] = q.astype(np.int32), colab.astype(np.int32)
         out[f"bev_{tag}_image"], out[f"bev_{tag}_bound_img"] = bl.astype(np.int32), np.array([bound, img])
-    # dataset-side filters: the methods are plain numpy on `self.*` attributes
-    Ds = _reference_class("utils/datasets/semantickitti_bev.py", "SemanticKITTIBEVDataset") \
-        if False else None  # (the dataset class pulls yaml / file lists in __init__; its two methods are replayed below)
-    src = open(rh.REF + "/utils/datasets/semantickitti_bev.py").read()
+    # dataset-side filter + augmentation: plain numpy on `self.*` attributes / module-level scipy
     import ast
-    tree = ast.parse(src)
-    fb = None
-    for n in ast.walk(tree):
-        if isinstance(n, ast.FunctionDef) and n.name == "filter_bounds":
-            fb = n
-            break
+    src = open(rh.REF + "/utils/datasets/semantickitti_bev.py").read()
+    fb = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "filter_bounds")
     ns = {"np": np}
     exec(compile(ast.Module(body=[fb], type_ignores=[]), "semantickitti_bev.py", "exec"), ns)
 
     class Self:
-        grid_bounds2d = [[-50.0, 50.0], [-50.0, 50.0], [-10, 8]]
-        mapping_boundaries = grid_bounds2d
+        grid_bounds = [[-60, 60], [-60, 60], [-10, 8]]  # semantickitti_bev.py:137
     rng = np.random.default_rng(11)
     cloud = np.concatenate([rng.uniform(-70, 70, (4000, 2)), rng.uniform(-12, 10, (4000, 1))], 1).astype(np.float32)
-    try:
-        keep = ns["filter_bounds"](Self(), cloud)
-        out["filter_points"], out["filter_keep"] = cloud, np.asarray(keep)
-        out["filter_source"] = np.array(ast.get_source_segment(src, fb).count("\n"))  # (size of what was replayed)
-    except Exception as e:  # attribute names differ from the survey: keep the fixture honest
-        print("filter_bounds not replayed:", repr(e))
+    cloud[:200, :2] = rng.uniform(-3.5, 3.5, (200, 2)).astype(np.float32)  # around the ego box
+    out["filter_points"], out["filter_keep"] = cloud, np.asarray(ns["filter_bounds"](Self(), cloud))
+    from scipy.linalg import expm, norm
+    asrc = open(rh.REF + "/utils/common/augmentation.py").read()
+    ans = {"np": np, "expm": expm, "norm": norm}
+    for node in ast.parse(asrc).body:
+        if isinstance(node, ast.ClassDef) and node.name in ("RandomRotation", "RandomScale"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "augmentation.py", "exec"), ans)
+    np.random.seed(1234)  # configs/lidog/single/semantickitti.yaml:32
+    pts32 = rng.uniform(-40, 40, (3000, 3)).astype(np.float32)
+    aug = ans["RandomScale"](0.95, 1.05)(ans["RandomRotation"]()(pts32.copy()))  # order of train_lidog's Compose
+    out["aug_points"], out["aug_result"] = pts32, np.asarray(aug)
+    assert out["aug_result"].dtype == np.float64  # float32 @ float64: what sparse_quantize then receives
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_step_products.npz"), **out)
     print({k: getattr(v, "shape", v) for k, v in out.items()})
 
