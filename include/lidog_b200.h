@@ -126,10 +126,15 @@ typedef struct lgConvPlan {
 /* Neighbour table for out voxel o and offset k (x fastest; odd size centred, even size 0-based;
  * offsets scaled by offset_scale = input tensor stride):  nbr[k][o] = row of (o + off_k) in table_in.
  * Replaces ME's kernel-map generation implied by every MinkowskiConvolution
- * (utils/models/minkunet_bev.py:57-123,410-442).  n_slots = round_up(n_out, LG_TILE_ROWS). */
+ * (utils/models/minkunet_bev.py:57-123,410-442).  n_slots = round_up(n_out, LG_TILE_ROWS).
+ * in_row_offset: subtracted from every row the table returns -- the table may index a larger coordinate set of which
+ *   the gathered matrix is a contiguous slice (multi-source batches sharing one hashed index,
+ *   utils/pipelines/trainer_lighting_2d_multi.py:146-167); 0 otherwise.
+ * same_set != 0 declares that out_coords4 IS the set the table indexes (3x3x3 / 5x5x5 same-stride maps): pair
+ *   (k, o -> i) then implies (K-1-k, i -> o), and only half of the offsets are probed. */
 int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
-                  int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int64_t n_slots, uint32_t* tile_mask,
-                  void* stream);
+                  int32_t kernel_size, int32_t offset_scale, int32_t in_row_offset, int32_t same_set, int32_t* nbr,
+                  int64_t n_slots, uint32_t* tile_mask, void* stream);
 
 /* Same neighbour table with the rows REORDERED so that rows with the same neighbour pattern share a
  * 128-row tile (kernel_size <= 3): slot s serves result row out_row[s] (-1 = padding) and gathers
@@ -138,8 +143,9 @@ int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_
  * then issue ~2.4x fewer (tile, offset) units on LiDAR scans.  Same reference contract as lg_kernel_map. */
 size_t lg_kernel_map_sorted_workspace(int64_t n_out, int32_t kernel_size);
 int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
-                         int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int32_t* out_row, int64_t n_slots,
-                         uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream);
+                         int32_t kernel_size, int32_t offset_scale, int32_t in_row_offset, int32_t same_set,
+                         int32_t* nbr, int32_t* out_row, int64_t n_slots, uint32_t* tile_mask, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 size_t lg_scan_workspace(int64_t n_items);
 
@@ -155,8 +161,9 @@ int lg_kernel_map_pairs(const int32_t* nbr, int32_t K, int64_t n_slots, int32_t*
  *   n_slots must be >= round_up(n_fine, 128) + 8 * 128;  slots_used int64[1] receives the used count.
  * Replaces ME's transposed kernel map (utils/models/minkunet_bev.py:89,96,103,110). */
 int lg_kernel_map_up2(const int32_t* fine_coords4, const int64_t* parent_of_fine, int64_t n_fine,
-                      int32_t fine_stride, int32_t* gather, int32_t* out_row, uint32_t* tile_mask, int64_t n_slots,
-                      int64_t* slots_used, void* workspace, size_t workspace_bytes, void* stream);
+                      int32_t fine_stride, int64_t parent_offset /* subtracted from the parent ids */, int32_t* gather,
+                      int32_t* out_row, uint32_t* tile_mask, int64_t n_slots, int64_t* slots_used, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ sparse convolution */
 

@@ -62,12 +62,12 @@ SIGNATURES = {
     "lg_coords_unique_workspace": (_sz, [_i64]),
     "lg_coords_unique": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "lg_coords_pyramid": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, C.POINTER(_i32), C.POINTER(LevelOut), _vp, _vp, _vp]),
-    "lg_kernel_map": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "lg_kernel_map": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "lg_kernel_map_sorted_workspace": (_sz, [_i64, _i32]),
-    "lg_kernel_map_sorted": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "lg_kernel_map_sorted": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "lg_scan_workspace": (_sz, [_i64]),
     "lg_kernel_map_pairs": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "lg_kernel_map_up2": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "lg_kernel_map_up2": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "lg_conv_gemm_simt": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "lg_conv_wgrad_workspace": (_sz, [_PP, _i32, _i32]),
     "lg_conv_wgrad_simt": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),

@@ -7,6 +7,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "runtime.cuh"
 #include "scan.cuh"
 
 namespace lg {
@@ -15,7 +16,7 @@ constexpr int kMaxMaskWords = 4;  // K <= 128 (5^3 = 125)
 
 __global__ void __launch_bounds__(LG_TILE_ROWS)
     k_neighbors(const HashSlot* __restrict__ table, unsigned long long mask, const int4* __restrict__ out_coords,
-                int64_t n_out, int ksize, int scale, int K, int mask_words, int32_t* __restrict__ nbr,
+                int64_t n_out, int ksize, int scale, int row_offset, int K, int mask_words, int32_t* __restrict__ nbr,
                 int64_t n_slots, uint32_t* __restrict__ tile_mask, uint32_t* __restrict__ row_mask,
                 unsigned int* __restrict__ k_count) {
   __shared__ uint32_t s_mask[kMaxMaskWords];
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
         if (valid) {
           int x = c.y + (base + ix) * scale, y = c.z + (base + iy) * scale, z = c.w + (base + iz) * scale;
           if (coord_in_range(c.x, x, y, z)) r = hash_lookup(table, mask, pack_key(c.x, x, y, z));
+          if (r >= 0) r -= row_offset;  // the table may index a larger set this one is a contiguous slice of
         }
         nbr[(int64_t)k * n_slots + o] = r;
         const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
@@ -54,6 +56,96 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
   }
   __syncthreads();
   if (threadIdx.x < mask_words) tile_mask[(int64_t)blockIdx.x * mask_words + threadIdx.x] = s_mask[threadIdx.x];
+}
+
+// Same-set maps (odd kernel, output set == the set the table indexes): pair (k, o -> i) exists iff pair
+// (K-1-k, i -> o) does, so only the first half of the offsets is probed and every hit also writes its mirror entry.
+// k_neighbors is issue-bound on the probes (ncu: ~4.5 warp instructions per probe-lane), so half the probes is close
+// to half the time; the mirror entries cost one scattered 4-byte store and an atomicOr on the tile / row masks per
+// hit.  Requires: nbr[(K/2+1..K-1)][*] preset to -1, tile_mask and row_mask preset to 0 (the launcher does it).
+// Every table entry is written exactly once with a value that does not depend on the schedule: deterministic.
+__global__ void __launch_bounds__(LG_TILE_ROWS)
+    k_neighbors_sym(const HashSlot* __restrict__ table, unsigned long long mask, const int4* __restrict__ out_coords,
+                    int64_t n_out, int ksize, int scale, int row_offset, int K, int mask_words,
+                    int32_t* __restrict__ nbr, int64_t n_slots, uint32_t* __restrict__ tile_mask,
+                    uint32_t* __restrict__ row_mask, unsigned int* __restrict__ k_count) {
+  __shared__ uint32_t s_mask[kMaxMaskWords];
+  if (threadIdx.x < kMaxMaskWords) s_mask[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t o = (int64_t)blockIdx.x * LG_TILE_ROWS + threadIdx.x;
+  const bool valid = o < n_out;
+  const int4 c = valid ? out_coords[o] : make_int4(0, 0, 0, 0);
+  const int base = -(ksize / 2), half = K / 2;
+  uint32_t wmask[kMaxMaskWords] = {0, 0, 0, 0};
+  uint32_t rmask = 0;
+  int k = 0;
+  for (int iz = 0; iz < ksize && k < half; ++iz)
+    for (int iy = 0; iy < ksize && k < half; ++iy)
+      for (int ix = 0; ix < ksize && k < half; ++ix, ++k) {
+        int r = -1;
+        if (valid) {
+          const int x = c.y + (base + ix) * scale, y = c.z + (base + iy) * scale, z = c.w + (base + iz) * scale;
+          if (coord_in_range(c.x, x, y, z)) r = hash_lookup(table, mask, pack_key(c.x, x, y, z));
+          if (r >= 0) r -= row_offset;
+        }
+        nbr[(int64_t)k * n_slots + o] = r;
+        const int km = K - 1 - k;
+        if (r >= 0) {  // the mirror pair: voxel r sees o through offset K-1-k
+          nbr[(int64_t)km * n_slots + r] = (int32_t)o;
+          atomicOr(&tile_mask[(int64_t)(r / LG_TILE_ROWS) * mask_words + (km >> 5)], 1u << (km & 31));
+          if (row_mask) atomicOr(&row_mask[r], 1u << (km & 31));
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
+        if (bal) wmask[k >> 5] |= 1u << (k & 31);
+        if (row_mask) {
+          rmask |= (r >= 0 ? 1u : 0u) << (k & 31);
+          if (bal && (threadIdx.x & 31) == 0) {
+            atomicAdd(&k_count[k], (unsigned)__popc(bal));
+            atomicAdd(&k_count[km], (unsigned)__popc(bal));
+          }
+        }
+      }
+  // centre offset: the voxel itself
+  nbr[(int64_t)half * n_slots + o] = valid ? (int32_t)o : -1;
+  {
+    const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+    if (bal) wmask[half >> 5] |= 1u << (half & 31);
+    if (row_mask) {
+      rmask |= (valid ? 1u : 0u) << (half & 31);
+      if (bal && (threadIdx.x & 31) == 0) atomicAdd(&k_count[half], (unsigned)__popc(bal));
+    }
+  }
+  if (row_mask && rmask) atomicOr(&row_mask[o], rmask);
+  if ((threadIdx.x & 31) == 0) {
+    for (int w = 0; w < mask_words; ++w)
+      if (wmask[w]) atomicOr(&s_mask[w], wmask[w]);
+  }
+  __syncthreads();
+  if (threadIdx.x < mask_words && s_mask[threadIdx.x])
+    atomicOr(&tile_mask[(int64_t)blockIdx.x * mask_words + threadIdx.x], s_mask[threadIdx.x]);
+}
+
+static int launch_neighbors(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
+                            int kernel_size, int offset_scale, int row_offset, int same_set, int K, int words,
+                            int32_t* nbr, int64_t n_slots, uint32_t* tile_mask, uint32_t* row_mask,
+                            unsigned int* k_count, cudaStream_t stream) {
+  const unsigned grid = (unsigned)(n_slots / LG_TILE_ROWS);
+  static const int sym_on = env_int("LIDOG_KMAP_SYM", 1);
+  if (same_set && sym_on && (kernel_size & 1) && kernel_size >= 3) {
+    const int half = K / 2;
+    LG_CUDA_OK(cudaMemsetAsync(nbr + (int64_t)(half + 1) * n_slots, 0xFF, sizeof(int32_t) * (size_t)half * n_slots, stream));
+    LG_CUDA_OK(cudaMemsetAsync(tile_mask, 0, sizeof(uint32_t) * (size_t)grid * words, stream));
+    if (row_mask) LG_CUDA_OK(cudaMemsetAsync(row_mask, 0, sizeof(uint32_t) * (size_t)n_slots, stream));
+    k_neighbors_sym<<<grid, LG_TILE_ROWS, 0, stream>>>((const HashSlot*)table_in, (unsigned long long)(capacity_in - 1),
+                                                       (const int4*)out_coords4, n_out, kernel_size, offset_scale,
+                                                       row_offset, K, words, nbr, n_slots, tile_mask, row_mask, k_count);
+  } else {
+    k_neighbors<<<grid, LG_TILE_ROWS, 0, stream>>>((const HashSlot*)table_in, (unsigned long long)(capacity_in - 1),
+                                                   (const int4*)out_coords4, n_out, kernel_size, offset_scale, row_offset,
+                                                   K, words, nbr, n_slots, tile_mask, row_mask, k_count);
+  }
+  LG_LAUNCH_OK();
+  return LG_OK;
 }
 
 // ---- ME-format pair lists: flatten [K][n_slots], keep entries >= 0 (order = (k, out) ascending)
@@ -100,6 +192,7 @@ struct ChildSink {  // pass 1: only the per-k starts
 };
 struct ChildFill {
   const int64_t* parent;
+  int64_t parent_offset;  // the parent ids index a larger set this coarse level is a contiguous slice of
   int64_t n;
   const int* k_start;      // [9] (k_start[8] = n)
   const int* k_slot_base;  // [9] padded segment starts
@@ -109,7 +202,7 @@ struct ChildFill {
     if (!f) return;
     const int64_t k = i / n, r = i - k * n;
     const int slot = k_slot_base[k] + (prefix - k_start[k]);
-    gather[slot] = (int32_t)parent[r];
+    gather[slot] = (int32_t)(parent[r] - parent_offset);
     out_row[slot] = (int32_t)r;
   }
 };
@@ -192,8 +285,8 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
 using namespace lg;
 
 extern "C" int lg_kernel_map(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
-                             int32_t kernel_size, int32_t offset_scale, int32_t* nbr, int64_t n_slots,
-                             uint32_t* tile_mask, void* stream) {
+                             int32_t kernel_size, int32_t offset_scale, int32_t in_row_offset, int32_t same_set,
+                             int32_t* nbr, int64_t n_slots, uint32_t* tile_mask, void* stream) {
   LG_CHECK_ARG(kernel_size >= 1 && kernel_size <= 5, "lg_kernel_map: kernel_size %d not in [1,5]", kernel_size);
   LG_CHECK_ARG(n_out >= 0 && n_slots == round_up(n_out, LG_TILE_ROWS), "lg_kernel_map: n_slots must be round_up(n_out,128)");
   LG_CHECK_ARG(capacity_in >= 1024 && (capacity_in & (capacity_in - 1)) == 0, "lg_kernel_map: bad capacity");
@@ -201,11 +294,8 @@ extern "C" int lg_kernel_map(const void* table_in, int64_t capacity_in, const in
   LG_CHECK_ARG(table_in && out_coords4 && nbr && tile_mask, "lg_kernel_map: null pointer");
   const int K = kernel_size * kernel_size * kernel_size;
   const int words = (K + 31) / 32;
-  k_neighbors<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, (cudaStream_t)stream>>>(
-      (const HashSlot*)table_in, (unsigned long long)(capacity_in - 1), (const int4*)out_coords4, n_out, kernel_size,
-      offset_scale, K, words, nbr, n_slots, tile_mask, nullptr, nullptr);
-  LG_LAUNCH_OK();
-  return LG_OK;
+  return launch_neighbors(table_in, capacity_in, out_coords4, n_out, kernel_size, offset_scale, in_row_offset, same_set,
+                          K, words, nbr, n_slots, tile_mask, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 namespace {
@@ -249,9 +339,9 @@ extern "C" size_t lg_kernel_map_sorted_workspace(int64_t n_out, int32_t kernel_s
 }
 
 extern "C" int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, const int32_t* out_coords4,
-                                    int64_t n_out, int32_t kernel_size, int32_t offset_scale, int32_t* nbr,
-                                    int32_t* out_row, int64_t n_slots, uint32_t* tile_mask, void* workspace,
-                                    size_t workspace_bytes, void* stream_) {
+                                    int64_t n_out, int32_t kernel_size, int32_t offset_scale, int32_t in_row_offset,
+                                    int32_t same_set, int32_t* nbr, int32_t* out_row, int64_t n_slots,
+                                    uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LG_CHECK_ARG(kernel_size >= 1 && kernel_size <= 3, "lg_kernel_map_sorted: kernel_size %d not in [1,3]", kernel_size);
   LG_CHECK_ARG(n_out >= 0 && n_slots == round_up(n_out, LG_TILE_ROWS),
@@ -265,10 +355,9 @@ extern "C" int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, c
   const int K = kernel_size * kernel_size * kernel_size;
   SortedWs w = carve_sorted(workspace, n_out, K);
   LG_CUDA_OK(cudaMemsetAsync(w.k_count, 0, 4 * 32, stream));
-  k_neighbors<<<(unsigned)(n_slots / LG_TILE_ROWS), LG_TILE_ROWS, 0, stream>>>(
-      (const HashSlot*)table_in, (unsigned long long)(capacity_in - 1), (const int4*)out_coords4, n_out, kernel_size,
-      offset_scale, K, 1, w.nbr_nat, n_slots, w.nat_tile_mask, w.row_mask, w.k_count);
-  LG_LAUNCH_OK();
+  int rc = launch_neighbors(table_in, capacity_in, out_coords4, n_out, kernel_size, offset_scale, in_row_offset, same_set,
+                            K, 1, w.nbr_nat, n_slots, w.nat_tile_mask, w.row_mask, w.k_count, stream);
+  if (rc) return rc;
   k_sort_keys<<<(unsigned)ceil_div(n_out, 256), 256, 0, stream>>>(w.row_mask, w.k_count, K, n_out, w.keys_in,
                                                                   w.vals_in);
   LG_LAUNCH_OK();
@@ -298,7 +387,8 @@ extern "C" int lg_kernel_map_pairs(const int32_t* nbr, int32_t K, int64_t n_slot
 }
 
 extern "C" int lg_kernel_map_up2(const int32_t* fine_coords4, const int64_t* parent_of_fine, int64_t n_fine,
-                                 int32_t fine_stride, int32_t* gather, int32_t* out_row, uint32_t* tile_mask,
+                                 int32_t fine_stride, int64_t parent_offset, int32_t* gather, int32_t* out_row,
+                                 uint32_t* tile_mask,
                                  int64_t n_slots, int64_t* slots_used, void* workspace, size_t workspace_bytes,
                                  void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -326,6 +416,6 @@ extern "C" int lg_kernel_map_up2(const int32_t* fine_coords4, const int64_t* par
   if (rc != LG_OK) return rc;
   k_up2_layout<<<1, 1, 0, stream>>>(k_start, n_fine, k_slot_base, tile_mask, n_slots / LG_TILE_ROWS, slots_used);
   LG_LAUNCH_OK();
-  ChildFill s2{parent_of_fine, n_fine, k_start, k_slot_base, gather, out_row};
+  ChildFill s2{parent_of_fine, parent_offset, n_fine, k_start, k_slot_base, gather, out_row};
   return device_scan(flag, s2, n, nullptr, scan_ws, stream);
 }

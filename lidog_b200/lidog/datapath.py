@@ -95,3 +95,27 @@ def prepare_scan(points: torch.Tensor, labels: torch.Tensor, in_radius: float = 
         m = bounds_mask(pts)
         pts, lab, kept = pts[m], lab[m], kept[m]
     return pts, lab, kept
+
+
+def mix3d_merge(source0: dict, source1: dict, voxel_size: float, ignore_label, ME=None) -> dict:
+    """Mix3D merge of two already voxelised samples (`merge_data`, utils/datasets/mix3D.py:43-87) on the samples'
+    device: the integer voxel coordinates of both samples go back to metric float32 (`coordinates * voxel_size`, a
+    torch int tensor times a python float = a float32 product, `:45-46`), are concatenated (`:60`) and re-quantised
+    with one hash build (`:67-72`); features / labels / sampled indices follow the first point of every merged voxel
+    (`:74-76`).  The float32 round trip makes floor(float32(c * 0.05) / 0.05) = c - 1 for ~6 % of the integers
+    (SURVEY.md 8a), so this is NOT the set union of the two voxel sets -- the arithmetic is reproduced, not shortcut.
+    `source*` = dict(coordinates int [N,3], features [N,C], sem_labels [N], sampled_idx [N], xyz, idx)."""
+    if ME is None:
+        from lidog_b200 import me as ME
+    c0, c1 = source0["coordinates"], source1["coordinates"]
+    metric = torch.cat([c0.to(torch.float32) * voxel_size, c1.to(torch.float32) * voxel_size], dim=0)
+    features = torch.cat([source0["features"], source1["features"]], dim=0)
+    sem_labels = torch.cat([source0["sem_labels"], source1["sem_labels"]], dim=0)
+    sampled_idx = torch.cat([source0["sampled_idx"], source1["sampled_idx"]], dim=0)
+    q, _, _, voxel_idx = ME.utils.sparse_quantize(metric, features, labels=sem_labels, ignore_label=ignore_label,
+                                                  quantization_size=voxel_size, return_index=True)
+    voxel_idx = torch.as_tensor(voxel_idx, device=features.device)
+    return dict(coordinates=torch.as_tensor(q), xyz=torch.cat([source0["xyz"], source1["xyz"]], dim=0),
+                features=features[voxel_idx], sem_labels=sem_labels[voxel_idx],
+                idx=torch.cat([source0["idx"].view(1, -1), source1["idx"].view(1, -1)], dim=0),
+                sampled_idx=sampled_idx[voxel_idx])

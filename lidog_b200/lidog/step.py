@@ -73,6 +73,25 @@ class LidogTrainer:
             cm = self.ME.CoordinateManager.from_quantized(q)  # share the voxelisation hash with the network
         return q["coords"], feats, sem_labels, bev_labels, cm
 
+    def voxelize_multi(self, sources):
+        """All source batches through ONE voxelisation / coordinate pyramid (one hashed voxel index and one host round
+        trip for the whole step), then one view of the shared coordinate manager per source
+        (`CoordinateManager.split`).  Backends without `split` (the CPU oracle) voxelise per source.
+        -> [(coords, feats, sem_labels, bev_labels, manager, batch_size), ...]"""
+        CM = getattr(self.ME, "CoordinateManager", None)
+        if CM is None or not hasattr(CM, "split"):
+            return [self.voxelize(p, l) + (len(p),) for p, l in sources]
+        sizes = [len(p) for p, _ in sources]
+        pts = [x for p, _ in sources for x in p]
+        lab = [x for _, l in sources for x in l]
+        coords, feats, sem_labels, bev_labels, cm = self.voxelize(pts, lab)
+        out, r0, b0 = [], 0, 0
+        for view, nb in zip(cm.split(sizes), sizes):
+            n = view.levels[1].n
+            out.append((view.levels[1].coords, feats[r0:r0 + n], sem_labels[r0:r0 + n], bev_labels[b0:b0 + nb], view, nb))
+            r0, b0 = r0 + n, b0 + nb
+        return out
+
     def forward_loss(self, coords, feats, sem_labels, bev_labels, batch_size=None, coordinate_manager=None):
         if coordinate_manager is not None:
             stensor = self.ME.SparseTensor(features=feats, coordinate_manager=coordinate_manager)
@@ -102,7 +121,7 @@ class LidogTrainer:
         total = sum_i source_weights[i] * (loss_3d_i + loss_bev_i), one backward, one optimizer step.
         `sources` = [(points_list, labels_list), ...] (two in the reference)."""
         assert len(sources) == len(self.source_weights), "one weight per source domain"
-        batches = [self.voxelize(p, l) + (len(p),) for p, l in sources]
+        batches = self.voxelize_multi(sources)
         self.optimizer.zero_grad(set_to_none=True)
         total = None
         for w, (coords, feats, sem_labels, bev_labels, cm, n) in zip(self.source_weights, batches):

@@ -119,12 +119,19 @@ def build_levels(coords: torch.Tensor, labels: torch.Tensor | None = None, ignor
 
 
 class Level:
-    """Coordinates of one tensor stride + their hash table."""
+    """Coordinates of one tensor stride + their hash table.
 
-    def __init__(self, coords, table, capacity, parent_of_finer=None):
+    A level may be a contiguous row SLICE of a larger indexed set (`CoordinateManager.split`: several source batches
+    voxelised and hashed together): `key_coords` are the rows as the shared table knows them (global batch index),
+    `coords` what the tensor shows (`.C`, batch index local to the source), `row_offset` the global row of local row 0
+    -- table hits and `parent_of_finer` entries are global and get the offset of their level subtracted."""
+
+    def __init__(self, coords, table, capacity, parent_of_finer=None, key_coords=None, row_offset=0):
         self.coords, self.table, self.capacity = coords, table, capacity
+        self.key_coords = coords if key_coords is None else key_coords
+        self.row_offset = int(row_offset)
         self.n = coords.shape[0]
-        self.parent_of_finer = parent_of_finer  # int64 [n_finer]: row here of every row of the finer level
+        self.parent_of_finer = parent_of_finer  # int64 [n_finer]: (global) row here of every row of the finer level
 
 
 class GatherPlan:
@@ -177,6 +184,41 @@ class CoordinateManager:
         self._adopt(levels, levels[0]["n"])
         return self
 
+    def split(self, batch_sizes):
+        """Per-source views of a manager built over the CONCATENATED batch of several sources (multi-source training,
+        utils/pipelines/trainer_lighting_2d_multi.py:146-167: one forward pass per source through the same model).
+        The hash tables, coordinate levels and one host round trip are shared; each view owns a contiguous row range
+        of every level (rows are batch-ordered at every stride) and its own gather plans, built against the shared
+        tables with the row offset of its slice.  -> list of CoordinateManager, one per entry of `batch_sizes`."""
+        strides = sorted(self.levels)
+        bounds = torch.tensor([sum(batch_sizes[:i]) for i in range(len(batch_sizes) + 1)], dtype=torch.int32,
+                              device=self.device)
+        cuts = torch.stack([torch.searchsorted(self.levels[ts].coords[:, 0].contiguous(), bounds) for ts in strides])
+        cuts = cuts.tolist()  # one host round trip for all levels and sources
+        views = []
+        for s in range(len(batch_sizes)):
+            v = CoordinateManager.__new__(CoordinateManager)
+            v.device, v.levels, v.plans = self.device, {}, {}
+            v.input_unique_map = v.input_inverse_map = None
+            v.had_duplicates = False
+            v.batch_size = int(batch_sizes[s])
+            b0 = sum(batch_sizes[:s])
+            for li, ts in enumerate(strides):
+                lv = self.levels[ts]
+                r0, r1 = cuts[li][s], cuts[li][s + 1]
+                key = lv.key_coords[r0:r1]
+                local = key.clone()
+                if b0:
+                    local[:, 0] -= b0
+                parent = None
+                if lv.parent_of_finer is not None:
+                    f0, f1 = cuts[li - 1][s], cuts[li - 1][s + 1]
+                    parent = lv.parent_of_finer[f0:f1]
+                v.levels[ts] = Level(local, lv.table, lv.capacity, parent_of_finer=parent, key_coords=key,
+                                     row_offset=lv.row_offset + r0)
+            views.append(v)
+        return views
+
     def _stream(self):
         return torch._C._cuda_getCurrentRawStream(self.device.index)
 
@@ -186,6 +228,8 @@ class CoordinateManager:
             if ts < 2 or ts % 2:
                 raise ValueError(f"tensor stride {ts} cannot be derived by stride-2 downsampling")
             fine = self.level(ts // 2)
+            if fine.row_offset or fine.key_coords is not fine.coords:
+                raise NotImplementedError("a split view only has the strides its parent manager was built with")
             res = coords_unique(fine.coords, ts)
             self.levels[ts] = Level(res["coords"], res["table"], res["capacity"], parent_of_finer=res["inverse_map"])
         return self.levels[ts]
@@ -208,8 +252,9 @@ class CoordinateManager:
         n_slots = _round_up(n_out, cabi.TILE)
         nbr = torch.empty((K, max(n_slots, 1)), dtype=torch.int32, device=self.device)
         mask = torch.empty((max(n_slots // cabi.TILE, 1), (K + 31) // 32), dtype=torch.int32, device=self.device)
-        cabi.check(L.lg_kernel_map(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out, ksize,
-                                   scale, cabi.ptr(nbr), n_slots, cabi.ptr(mask), self._stream()), "lg_kernel_map")
+        cabi.check(L.lg_kernel_map(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.key_coords), n_out, ksize,
+                                   scale, lvl_in.row_offset, 1 if lvl_in is lvl_out else 0, cabi.ptr(nbr), n_slots,
+                                   cabi.ptr(mask), self._stream()), "lg_kernel_map")
         return GatherPlan(nbr, n_slots, None, mask, K, n_slots, n_out, lvl_in.n)
 
     def _sorted_plan(self, lvl_in: Level, lvl_out: Level, ksize: int, scale: int) -> GatherPlan:
@@ -224,9 +269,10 @@ class CoordinateManager:
         mask = torch.empty((max(n_slots // cabi.TILE, 1), 1), dtype=torch.int32, device=self.device)
         ws_bytes = L.lg_kernel_map_sorted_workspace(n_out, ksize)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        cabi.check(L.lg_kernel_map_sorted(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.coords), n_out,
-                                          ksize, scale, cabi.ptr(nbr), cabi.ptr(out_row), n_slots, cabi.ptr(mask),
-                                          cabi.ptr(ws), ws_bytes, self._stream()), "lg_kernel_map_sorted")
+        cabi.check(L.lg_kernel_map_sorted(cabi.ptr(lvl_in.table), lvl_in.capacity, cabi.ptr(lvl_out.key_coords), n_out,
+                                          ksize, scale, lvl_in.row_offset, 1 if lvl_in is lvl_out else 0, cabi.ptr(nbr),
+                                          cabi.ptr(out_row), n_slots, cabi.ptr(mask), cabi.ptr(ws), ws_bytes,
+                                          self._stream()), "lg_kernel_map_sorted")
         return GatherPlan(nbr, n_slots, out_row, mask, K, n_slots, n_out, lvl_in.n)
 
     def _plan_same(self, ts_in, ts_out, ksize):
@@ -261,8 +307,8 @@ class CoordinateManager:
         ws_bytes = L.lg_scan_workspace(8 * n_fine) + 256
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         cabi.check(L.lg_kernel_map_up2(cabi.ptr(fine.coords), cabi.ptr(coarse.parent_of_finer), n_fine, ts_out,
-                                       cabi.ptr(gather), cabi.ptr(out_row), cabi.ptr(mask), n_slots, cabi.ptr(used),
-                                       cabi.ptr(ws), ws_bytes, self._stream()), "lg_kernel_map_up2")
+                                       coarse.row_offset, cabi.ptr(gather), cabi.ptr(out_row), cabi.ptr(mask), n_slots,
+                                       cabi.ptr(used), cabi.ptr(ws), ws_bytes, self._stream()), "lg_kernel_map_up2")
         return GatherPlan(gather, 0, out_row, mask, 8, n_slots, n_fine, coarse.n)
 
     def _plan_identity(self, ts_in, ts_out, ksize):

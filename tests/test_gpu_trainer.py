@@ -116,3 +116,36 @@ def test_training_step_matches_oracle(cuda, mode, tol, head_tf32):
         assert torch.isfinite(p).all(), name
         moved = max(moved, float((p.detach().cpu() - state[name]).abs().max()))
     assert 0.5e-3 < moved < 2e-3, moved
+
+
+def test_multi_source_step_on_one_shared_coordinate_manager_matches_oracle(cuda):
+    """PLTTrainer2DMulti.training_step (trainer_lighting_2d_multi.py:135-199): one pass per source domain through the
+    same model, here on views of ONE coordinate manager built over both batches (`LidogTrainer.voxelize_multi`),
+    against the oracle trainer, which voxelises each source separately."""
+    import MinkowskiEngine as ME
+    from lidog_b200.lidog import model as M, step
+    from oracle import me_cpu
+    from oracle.me_cpu.bevfn import sparse2super as o_s2s
+    pts, lab = _batch()
+    sources = [([pts[0]], [lab[0]]), ([pts[1], pts[0][::2].copy()], [lab[1], lab[0][::2].copy()])]
+    torch.manual_seed(0)
+    ref_net = M.MinkUNet34BEV(1, 7, ME=me_cpu, bev_fn=o_s2s, mapping_bound_2d=30.0)
+    state = {k: v.clone() for k, v in ref_net.state_dict().items()}
+    ref = step.LidogTrainer(ref_net, num_classes=7, shape="nuscenes", ME=me_cpu)
+    to = lambda src, dev: [([torch.from_numpy(p).to(dev) for p in P], [torch.from_numpy(l).to(dev) for l in Lb]) for P, Lb in src]
+    loss_o = ref.training_step_multi(to(sources, "cpu"))
+    net = M.MinkUNet34BEV(1, 7, mapping_bound_2d=30.0)
+    net.load_state_dict(state)
+    net = net.to(cuda)
+    tr = step.LidogTrainer(net, num_classes=7, shape="nuscenes")
+    batches = tr.voxelize_multi(to(sources, cuda))
+    assert batches[0][4] is not batches[1][4] and batches[0][4].levels[1].table is batches[1][4].levels[1].table
+    o_batches = [ref.voxelize(P, Lb) for P, Lb in to(sources, "cpu")]
+    for (c, f, sem, bev, cm, nb), (co, fo, semo, bevo, cmo) in zip(batches, o_batches):
+        assert torch.equal(c.cpu(), co.to(torch.int32)) and torch.equal(sem.cpu(), semo) and torch.equal(bev.cpu(), bevo)
+    loss = tr.training_step_multi(to(sources, cuda))
+    torch.cuda.synchronize()
+    record("training_step_multi", loss=float(loss), loss_oracle=float(loss_o), diff=abs(float(loss) - float(loss_o)))
+    assert abs(float(loss) - float(loss_o)) <= 1e-4 * max(1.0, abs(float(loss_o)))
+    moved = max(float((p.detach().cpu() - state[k]).abs().max()) for k, p in net.named_parameters())
+    assert 0.5e-3 < moved < 2e-3, moved

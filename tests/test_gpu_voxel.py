@@ -217,3 +217,48 @@ def test_stride2_plans_match_oracle(cuda):
             assert np.array_equal(gk[:, 0], ri) and np.array_equal(gk[:, 1], ro), k
             seen += len(ro)
         assert seen == fine.shape[0]
+
+
+def test_split_views_of_a_shared_index_equal_independent_managers(cuda):
+    """Multi-source step (trainer_lighting_2d_multi.py:146-167): both source batches are voxelised and hashed ONCE;
+    `CoordinateManager.split` hands each forward pass a view whose levels and gather plans must be bit-identical to
+    those of a manager built from that source alone."""
+    from lidog_b200.me.coords import CoordinateManager
+    rng = np.random.default_rng(8)
+    a, b = random_voxels(rng, 9000, batch=2), random_voxels(rng, 7000, batch=3)
+    both = np.concatenate([a, b + np.array([[2, 0, 0, 0]], np.int32)], 0)
+    shared = _manager(both, cuda)
+    views = shared.split([2, 3])
+    for view, src in zip(views, (a, b)):
+        alone = _manager(src, cuda)
+        for ts in (1, 2, 4, 8, 16):
+            assert torch.equal(view.levels[ts].coords, alone.levels[ts].coords), ts
+            if ts > 1:
+                got = view.levels[ts].parent_of_finer - view.levels[ts].row_offset
+                assert torch.equal(got, alone.levels[ts].parent_of_finer), ts
+        for key in (("same", 1, 1, 3), ("same", 1, 1, 5), ("same_sorted", 1, 1, 3), ("same_sorted", 4, 4, 3),
+                    ("down_sorted", 1, 2, 2), ("down", 2, 4, 2), ("up", 2, 1, 2), ("up", 8, 4, 2), ("identity", 2, 2, 1)):
+            p, q = view.plan(*key), alone.plan(*key)
+            assert (p.n_out, p.n_in, p.n_slots, p.K) == (q.n_out, q.n_in, q.n_slots, q.K), key
+            assert torch.equal(p.nbr, q.nbr), key
+            assert torch.equal(p.tile_mask, q.tile_mask), key
+            assert (p.out_row is None) == (q.out_row is None) and (p.out_row is None or torch.equal(p.out_row, q.out_row)), key
+
+
+def test_mix3d_merge_on_the_device_matches_the_oracle(cuda):
+    """datapath.mix3d_merge (utils/datasets/mix3D.py:43-87) with the CUDA voxelisation == the same function on the
+    oracle shim (which tests/test_reference_unchanged.py pins to the reference's own merge_data), bit exact."""
+    from lidog_b200.lidog import datapath, synth
+    from oracle import me_cpu
+
+    def sample(seed, idx):
+        pts, lab = synth.make_scan(seed, "nuscenes")
+        q, f, _, vidx, _ = ov.sparse_quantize(pts, np.ones((len(pts), 1), np.float32), lab, -1, True, True, False, 0.05)
+        return dict(coordinates=torch.from_numpy(q), xyz=torch.from_numpy(pts[vidx]), features=torch.from_numpy(f),
+                    sem_labels=torch.from_numpy(lab[vidx]), sampled_idx=torch.from_numpy(vidx), idx=torch.tensor(idx))
+    s0, s1 = sample(41, 0), sample(42, 1)
+    ref = datapath.mix3d_merge(s0, s1, 0.05, -1, ME=me_cpu)
+    dev = lambda s: {k: v.to(cuda) for k, v in s.items()}
+    got = datapath.mix3d_merge(dev(s0), dev(s1), 0.05, -1)
+    for k in ("coordinates", "features", "sem_labels", "sampled_idx"):
+        assert got[k].is_cuda and torch.equal(got[k].cpu(), torch.as_tensor(ref[k])), k

@@ -216,3 +216,33 @@ def test_reference_collation_and_training_step_run_unchanged_and_equal_the_mirro
     mir.optimizer.step()
     moved = max(float((p.detach() - net_r.state_dict()[k]).abs().max()) for k, p in net_m.named_parameters())
     assert moved <= 5e-4, moved  # both took the same Adam(lr 1e-3, wd 1e-4) step (|update| ~ 1e-3 each)
+
+
+def _voxelised_sample(seed, r, idx):
+    from oracle import voxel as ov
+    pts, lab = _scan(seed, r)
+    q, f, _, vidx, inv = ov.sparse_quantize(pts, np.ones((len(pts), 1), np.float32), lab, -1, True, True, False, 0.05)
+    return dict(coordinates=torch.from_numpy(q), xyz=torch.from_numpy(pts[vidx]), features=torch.from_numpy(f),
+                sem_labels=torch.from_numpy(lab[vidx]), sampled_idx=torch.from_numpy(vidx), idx=torch.tensor(idx),
+                inverse_map=torch.from_numpy(inv))
+
+
+def test_reference_mix3d_merge_equals_the_device_merge():
+    """`merge_data` (utils/datasets/mix3D.py:43-87), run unchanged on the shim, vs datapath.mix3d_merge."""
+    import ast
+    import types
+    from oracle import me_cpu
+    from lidog_b200.lidog import datapath
+    src = open(rh.REF + "/utils/datasets/mix3D.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "merge_data")
+    ns = {"np": np, "torch": torch, "ME": me_cpu}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), rh.REF + "/utils/datasets/mix3D.py", "exec"), ns)
+    s0, s1 = _voxelised_sample(31, 9.0, 0), _voxelised_sample(32, 9.0, 1)
+    ref = ns["merge_data"](types.SimpleNamespace(voxel_size=0.05, ignore_label=-1), s0, s1)
+    got = datapath.mix3d_merge(s0, s1, 0.05, -1, ME=me_cpu)
+    assert len(ref["coordinates"]) < len(s0["coordinates"]) + len(s1["coordinates"])  # overlapping voxels merged
+    for k in ("coordinates", "features", "sem_labels", "sampled_idx", "xyz", "idx"):
+        assert torch.equal(torch.as_tensor(ref[k]), torch.as_tensor(got[k])), k
+    # the float32 round trip is in there: the merged set is not the plain union of the two integer sets
+    union = np.unique(np.concatenate([s0["coordinates"].numpy(), s1["coordinates"].numpy()]), axis=0)
+    assert not np.array_equal(np.unique(np.asarray(ref["coordinates"]), axis=0), union)
