@@ -7,6 +7,7 @@
 tag=$1; shift
 mkdir -p gpurun_out
 O=gpurun_out/${tag}
+# gpurun merges gpurun_out/ back only while it stays under 64 MiB: reports are exported to text on the box and removed
 for step in "$@"; do
   echo "=== $step" | tee -a ${O}_steps.log
   case $step in
@@ -31,11 +32,20 @@ for step in "$@"; do
                 --log-file ${O}_launches.csv python bench.py --ncu > ${O}_ncu1.log 2>&1
               python tools/launch_summary.py ${O}_launches.csv > ${O}_launch_summary.txt 2>&1; head -45 ${O}_launch_summary.txt ;;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm2 -s 58 -c 2 \
-                -o ${O}_ncu_gemm2 -f python bench.py --ncu > ${O}_ncu2.log 2>&1; ls -la ${O}_ncu_gemm2.ncu-rep ;;
+                -o ${O}_ncu_gemm2 -f python bench.py --ncu > ${O}_ncu2.log 2>&1
+              python tools/ncu_summary.py ${O}_ncu_gemm2.ncu-rep > ${O}_ncu_gemm2.txt; ncu -i ${O}_ncu_gemm2.ncu-rep --page source --csv > ${O}_ncu_gemm2_source.csv 2>/dev/null
+              ls -la ${O}_ncu_gemm2.*; rm -f ${O}_ncu_gemm2.ncu-rep ;;
     ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_wgrad -s 0 -c 2 \
-                -o ${O}_ncu_wgrad2 -f python bench.py --ncu > ${O}_ncu3.log 2>&1; ls -la ${O}_ncu_wgrad2.ncu-rep ;;
+                -o ${O}_ncu_wgrad2 -f python bench.py --ncu > ${O}_ncu3.log 2>&1
+              python tools/ncu_summary.py ${O}_ncu_wgrad2.ncu-rep > ${O}_ncu_wgrad2.txt; ncu -i ${O}_ncu_wgrad2.ncu-rep --page source --csv > ${O}_ncu_wgrad2_source.csv 2>/dev/null
+              ls -la ${O}_ncu_wgrad2.*; rm -f ${O}_ncu_wgrad2.ncu-rep ;;
     ncu_hbm)  timeout 900 ncu --set full --clock-control none --profile-from-start off \
-                -k regex:'k_bn_|k_neighbors|k_bev_|k_insert|k_conv_c1' -c 60 -o ${O}_ncu_hbm -f python bench.py --ncu > ${O}_ncu4.log 2>&1; ls -la ${O}_ncu_hbm.ncu-rep ;;
+                -k regex:'k_bn_|k_neighbors|k_insert|k_conv_c1|k_scan' -c 70 -o ${O}_ncu_hbm -f python bench.py --ncu > ${O}_ncu4.log 2>&1
+              python tools/ncu_summary.py ${O}_ncu_hbm.ncu-rep > ${O}_ncu_hbm_kernels.txt; ls -la ${O}_ncu_hbm*; rm -f ${O}_ncu_hbm.ncu-rep ;;
+    ncu_bev)  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+                -k regex:'k_bev_' -c 4 -o ${O}_ncu_bev -f python bench.py --ncu > ${O}_ncu5.log 2>&1
+              python tools/ncu_summary.py ${O}_ncu_bev.ncu-rep > ${O}_ncu_bev.txt; ncu -i ${O}_ncu_bev.ncu-rep --page source --csv > ${O}_ncu_bev_source.csv 2>/dev/null
+              ls -la ${O}_ncu_bev*; rm -f ${O}_ncu_bev.ncu-rep ;;
     sanitize) bash tools/sanitize.sh ${O} ;;
     *) echo "unknown step $step" ;;
   esac
