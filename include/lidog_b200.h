@@ -311,7 +311,9 @@ typedef struct lgBnBwdBranch {
 } lgBnBwdBranch;
 /* Backward of the above.  scales float[12]: [4i .. 4i+2] = {2^k, 2^-k, bound} of branch i's dx16. dres (nullable)
  * receives g = dy * [y > 0], the gradient of the plain residual. */
-int lg_bn_layer_backward(const float* dy, const float* y, int32_t relu, int64_t n, int32_t C, const lgBnBwdBranch* a,
+int lg_bn_layer_backward(const float* dy, int64_t dy_ld /* row pitch of dy in floats (>= C): the gradient of one input
+                         of ME.cat is a column slice of a wider matrix and is consumed in place */,
+                         const float* y, int32_t relu, int64_t n, int32_t C, const lgBnBwdBranch* a,
                          const lgBnBwdBranch* b /* nullable */, float* dres, int32_t fmt, float* scales,
                          const lgPeerCtx* peer /* nullable */, void* stream);
 
@@ -328,20 +330,21 @@ int lg_peer_sum(const double* local, int32_t n, void* const* peer_bufs, int32_t 
 
 /* ------------------------------------------------------------------ BEV projection */
 
-size_t lg_bev_workspace(int64_t n, int32_t batch_size, int32_t H, int32_t W);
+size_t lg_bev_workspace(int64_t n, int32_t C, int32_t batch_size, int32_t H, int32_t W);
 
 /* Fused point-to-BEV projection: pixel scatter + raw (H,W,C)->(C,H,W) re-view + MaxPool2d(pk,ps,pp),
  * never materialising the dense tensor.  Replaces MinkUNetBaseBEV.sparse2super + filter_bounds
  * (utils/models/minkunet_bev.py:158-230).  out: float [batch, C, h, w], h = (H + 2pp - pk)/ps + 1, stored
  * NCHW (layout 0) or NHWC / channels_last (layout 1: the same logical tensor, the memory order cuDNN's
  * tensor-op convolutions of the dense 2D head consume without staging copies).
- * workspace keeps the pixel map for lg_bev_backward. */
+ * workspace keeps the pixel map and the row-occupancy words for lg_bev_backward. */
 int lg_bev_forward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size, float bound,
                    float voxel_size, int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy,
                    int32_t layout, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (autograd of index_put_ + max_pool2d at minkunet_bev.py:217-221).
- * grad_feats [n, C] is fully written. */
+ * grad_feats [n, C] is fully written.  Atomic-free and bit-reproducible: every occupied cell sums the <= 4 windows it
+ * won in ascending (i, j) order (the order of torch's CPU max_pool2d backward). */
 int lg_bev_backward(const int32_t* coords4, const float* feats, int64_t n, int32_t C, int32_t batch_size,
                     int32_t H, int32_t W, int32_t pk, int32_t ps, int32_t pp, int32_t policy, int32_t layout,
                     const float* grad_out, float* grad_feats, const void* workspace, size_t workspace_bytes,

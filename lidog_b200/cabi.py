@@ -84,7 +84,7 @@ SIGNATURES = {
     "lg_debug_profile": (C.c_int, [_vp, C.c_int]),
     "lg_debug_trace": (C.c_int, [_vp]),
     "lg_bn_layer_forward": (C.c_int, [_PB, _PB, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _PPC, _vp]),
-    "lg_bn_layer_backward": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _PBB, _PBB, _vp, _i32, _vp, _PPC, _vp]),
+    "lg_bn_layer_backward": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i32, _PBB, _PBB, _vp, _i32, _vp, _PPC, _vp]),
     "lg_bn_workspace": (_sz, [_i64, _i32]),
     "lg_bn_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "lg_bn_finalize": (C.c_int, [_vp, C.c_double, _vp, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
@@ -96,7 +96,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _i32, _vp]),
     "lg_peer_exchange_bytes": (_sz, []),
     "lg_peer_sum": (C.c_int, [_vp, _i32, C.POINTER(C.c_void_p), _i32, _i32, C.c_uint64, _vp, _vp]),
-    "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32]),
+    "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _vp]),
     "lg_bev_backward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,

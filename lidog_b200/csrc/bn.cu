@@ -223,7 +223,9 @@ __device__ __forceinline__ float4 masked(float4 dy, float4 y, int relu) {
 __global__ void __launch_bounds__(kBnThreads)
     k_bn_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                    const float* __restrict__ st, const float* __restrict__ x2, const float* __restrict__ st2, int relu,
-                   int64_t n, int C, float* __restrict__ partial) {
+                   int64_t n, int C, float* __restrict__ partial, int64_t dy_ld4) {
+  // dy_ld4: row pitch of dy in float4 (C / 4 when dense; larger for a column slice of a wider matrix -- the gradient
+  // of one input of ME.cat arrives as such a view, and copying it first cost a pass)
   extern __shared__ float sm[];
   const RedGeom g = red_geom(n, C);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kBnThreads)
 #pragma unroll 4
     for (int64_t r = g.r0 + g.ry; r < g.r1; r += g.rpp) {
       const int64_t i = r * (C >> 2) + g.cq;
-      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + i),
+      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + r * dy_ld4 + g.cq),
                                relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z, relu);
       const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
       const float4 d = make_float4(v.x - mu.x, v.y - mu.y, v.z - mu.z, v.w - mu.w);
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(256)
                    float* __restrict__ dx, unsigned short* __restrict__ dx16, const float* __restrict__ scale,
                    float* __restrict__ dx2, unsigned short* __restrict__ dx2_16, const float* __restrict__ scale2,
                    float* __restrict__ dres, unsigned short* __restrict__ dres16, const float* __restrict__ scale_r,
-                   int fmt) {
+                   int fmt, int64_t dy_ld4) {
   const int64_t base = (int64_t)blockIdx.x * (256 * kBwdU) + threadIdx.x;
   const int Cq = C >> 2;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(256)
   for (int u = 0; u < kBwdU; ++u) {
     const int64_t i = base + u * 256;
     if (i < n4) {
-      gd[u] = __ldg(reinterpret_cast<const float4*>(dy) + i);
+      gd[u] = __ldg(reinterpret_cast<const float4*>(dy) + (dy_ld4 == Cq ? i : (i / Cq) * dy_ld4 + i % Cq));
       gy[u] = relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z;
       vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
       if (x2) vx2[u] = __ldg(reinterpret_cast<const float4*>(x2) + i);
@@ -668,7 +670,7 @@ extern "C" int lg_bn_bwd_stats(const float* dy, const float* y, const float* x, 
   LG_CHECK_ARG(workspace && workspace_bytes >= lg_bn_workspace(n, C), "lg_bn_bwd_stats: workspace too small");
   const int nb = bn_blocks(n);
   float* partial = (float*)workspace;
-  k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial);
+  k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
   LG_LAUNCH_OK();
   k_bn_bwd_reduce<<<ceil_div(6 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>(partial, nb, C, sums, maxes);
   LG_LAUNCH_OK();
@@ -712,7 +714,7 @@ extern "C" int lg_bn_bwd_apply(const float* dy, const float* y, const float* x, 
   const int64_t n4 = n * (C >> 2);
   k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256 * kBwdU), 256, 0, (cudaStream_t)stream_>>>(
       dy, y, x, stats, coef, x2, stats2, coef2, relu, n4, C, dx, (unsigned short*)dx16, scale, dx2,
-      (unsigned short*)dx2_16, scale2, dres, (unsigned short*)dres16, scale_r, fmt);
+      (unsigned short*)dx2_16, scale2, dres, (unsigned short*)dres16, scale_r, fmt, C >> 2);
   LG_LAUNCH_OK();
   return LG_OK;
 }
@@ -815,7 +817,7 @@ extern "C" int lg_bn_layer_forward(const lgBnBranch* a, const lgBnBranch* b, con
   return LG_OK;
 }
 
-extern "C" int lg_bn_layer_backward(const float* dy, const float* y, int32_t relu, int64_t n, int32_t C,
+extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float* y, int32_t relu, int64_t n, int32_t C,
                                     const lgBnBwdBranch* a, const lgBnBwdBranch* b, float* dres, int32_t fmt,
                                     float* scales /* [12]: a, b, residual */, const lgPeerCtx* peer, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -824,6 +826,8 @@ extern "C" int lg_bn_layer_backward(const float* dy, const float* y, int32_t rel
   LG_CHECK_ARG(n >= 0 && a && a->stats && scales && (!b || b->stats) &&
                    (n == 0 || (dy && a->x && a->dx && (!relu || y) && (!b || (b->x && b->dx)))),
                "lg_bn_layer_backward: null pointer");
+  LG_CHECK_ARG(dy_ld >= C && dy_ld % 4 == 0 && ((uintptr_t)dy & 15) == 0,
+               "lg_bn_layer_backward: dy needs a row pitch >= C that is a multiple of 4 floats and 16-byte alignment");
   int sm = 0;
   int* err = nullptr;
   rc = tc_runtime(&sm, &err);
@@ -838,7 +842,7 @@ extern "C" int lg_bn_layer_backward(const float* dy, const float* y, int32_t rel
   const int nb = bn_blocks(n);
   float* partial = (float*)arena_take(&ar, sizeof(float) * (size_t)kBnMaxBlocks * 6 * C);
   k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
-                                                          b ? b->stats : nullptr, relu, n, C, partial);
+                                                          b ? b->stats : nullptr, relu, n, C, partial, dy_ld >> 2);
   LG_LAUNCH_OK();
   BnBwdTail t;
   memset(&t, 0, sizeof(t));
@@ -873,7 +877,8 @@ extern "C" int lg_bn_layer_backward(const float* dy, const float* y, int32_t rel
     k_bn_bwd_apply<<<(unsigned)ceil_div(n4, 256 * kBwdU), 256, 0, stream>>>(
       dy, y, a->x, a->stats, t.br[0].coef, b ? b->x : nullptr, b ? b->stats : nullptr, b ? t.br[1].coef : nullptr, relu,
       n4, C, a->dx, (unsigned short*)a->dx16, use16 ? scales : nullptr, b ? b->dx : nullptr,
-      b ? (unsigned short*)b->dx16 : nullptr, (b && b->dx16) ? scales + 4 : nullptr, dres, nullptr, nullptr, fmt);
+      b ? (unsigned short*)b->dx16 : nullptr, (b && b->dx16) ? scales + 4 : nullptr, dres, nullptr, nullptr, fmt,
+      dy_ld >> 2);
   LG_LAUNCH_OK();
   return LG_OK;
 }

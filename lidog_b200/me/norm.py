@@ -151,8 +151,10 @@ class FusedBNFunction(torch.autograd.Function):
         L = cabi.lib()
         x, x2, y, st_a, st_b, w, w2 = ctx.saved_tensors
         relu, has_res, fmt, ex = ctx.meta
-        dy = dy.contiguous()
         n, C = x.shape
+        # the gradient of one input of ME.cat is a column slice of the concatenated gradient: consumed in place
+        if not (dy.stride(1) == 1 and dy.stride(0) >= C and dy.stride(0) % 4 == 0 and dy.data_ptr() % 16 == 0):
+            dy = dy.contiguous()
         dev = x.device
         use16 = fmt is not None
         d16 = _dtype16(fmt) if use16 else None
@@ -171,7 +173,8 @@ class FusedBNFunction(torch.autograd.Function):
             dx2, dx2_16, dgb2, br_b = branch(x2, st_b, w2)
             br_b = C_byref(br_b)
         dres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[6]) else None
-        cabi.check(L.lg_bn_layer_backward(dy.data_ptr(), cabi.ptr(y), 1 if relu else 0, n, C, C_byref(br_a), br_b,
+        cabi.check(L.lg_bn_layer_backward(dy.data_ptr(), dy.stride(0) if n > 1 else C, cabi.ptr(y), 1 if relu else 0, n, C,
+                                          C_byref(br_a), br_b,
                                           cabi.ptr(dres), fmt if use16 else 0, scales.data_ptr(),
                                           cabi.peer_ctx(ex, 1), cabi.stream_of(x)), "lg_bn_layer_backward")
         dw, db = dgb[0], dgb[1]

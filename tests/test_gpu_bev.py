@@ -32,6 +32,12 @@ def test_bev_matches_reference_golden(cuda, name):
     assert np.array_equal(out, GOLD[f"{name}/out"])
     ref = GOLD[f"{name}/grad_feats"]
     assert np.abs(g - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+    # the owner-computes backward sums a cell's windows in torch's CPU order: record whether the bits agree too
+    from tests.helpers import record
+    record("bev_backward_vs_reference", case=name, bit_exact=bool(np.array_equal(g, ref)),
+           max_abs_diff=float(np.abs(g - ref).max()))
+    _, g2 = _run(cuda, coords, feats, B, bound, "last", GOLD[f"{name}/grad_out"])
+    assert np.array_equal(g, g2)  # atomic-free: run-to-run deterministic
 
 
 def test_bev_full_size_image_golden(cuda):

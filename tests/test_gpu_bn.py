@@ -37,7 +37,7 @@ def layer_calls(request):
 
 
 @pytest.mark.parametrize("C", [32, 96, 256])
-@pytest.mark.parametrize("mode", ["bn_relu", "bn", "bn_res_relu", "bn_bn_relu"])
+@pytest.mark.parametrize("mode", ["bn_relu", "bn", "bn_res_relu", "bn_bn_relu", "bn_relu_cat"])
 def test_fused_bn_matches_torch(cuda, C, mode, layer_calls):
     ME, cm, n = _sparse(cuda, 5000)
     torch.manual_seed(C)
@@ -73,7 +73,11 @@ def test_fused_bn_matches_torch(cuda, C, mode, layer_calls):
             if mode != "bn":
                 out = relu(out)
             y = out.F
-            y.backward(gy.to(dt))
+            if mode == "bn_relu_cat":  # decoder: ME.cat(out, skip) -- the gradient comes back as a column slice
+                z = torch.cat([y, xs[2]], dim=1)
+                z.backward(torch.cat([gy, gy * 0.5], dim=1).to(dt))
+            else:
+                y.backward(gy.to(dt))
             grads = [t.grad for t in xs] + [a.bn.weight.grad, a.bn.bias.grad, b.bn.weight.grad, b.bn.bias.grad]
             stats = [a.bn.running_mean, a.bn.running_var, a.bn.num_batches_tracked]
             return y.detach(), grads, stats, out
