@@ -182,6 +182,8 @@ struct TileSmem {
   int* heads;         // [pairs][max_pix] pixel -> row head (or -1); valid for rows whose rowmask bit is set
   int* plo;           // [pairs] first pixel of the run
   uint32_t* rowmask;  // [kCG] bit (h - h_lo): scrambled row h of channel c' holds a voxel
+  unsigned short* lines;  // non-empty (c', i) lines of the tile: (cl << 8) | il; *n_lines = their count
+  int* n_lines;
   int* list;          // backward: occupied (pair, pixel) entries of the tile; list[-1] = their count
   unsigned char* arg; // backward: [kCG][kIBh][kJCh] winning cell of every window (position in the window, 255 = none)
 };
@@ -291,34 +293,39 @@ __device__ __forceinline__ void tile_transfer(const TileGeom& g, float* s_out, f
                                               int w_out, int i_first, int j_first, int rows, int cols, int cols_pitch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (layout && (C & 3) == 0) {
+    // thread = (column jl0 = tid / 8, float4 part = tid % 8); rows and the 33rd halo column are walked by loops --
+    // the flat-index form of this loop spent ~30 instructions per element on divisions by a run-time column count and
+    // was 60 % of all instructions of both pooling kernels (profiles/r02_b_ncu_bev.txt)
     const int parts = g.ncg >> 2;  // float4 per pixel (ncg is a multiple of 4 when C is)
-    const int total = rows * cols * 8;
-    for (int u = threadIdx.x; u < total; u += blockDim.x) {
-      const int part = u & 7, cell = u >> 3;
-      const int il = cell / cols, jl = cell - il * cols;
-      if (part >= parts) continue;
-      float4* ge = reinterpret_cast<float4*>(gptr + (((int64_t)g.b * h_out + i_first + il) * w_out + j_first + jl) * C +
-                                             g.c0 + 4 * part);
-      float4* se = reinterpret_cast<float4*>(s_out + (il * cols_pitch + jl) * kPitch + 4 * part);
-      if (STORE)
-        *ge = *se;
-      else
-        *se = *ge;
+    const int part = threadIdx.x & 7;
+    if (part < parts) {
+      for (int il = 0; il < rows; ++il) {
+        float* grow = gptr + (((int64_t)g.b * h_out + i_first + il) * w_out + j_first) * C + g.c0 + 4 * part;
+        float* srow = s_out + il * cols_pitch * kPitch + 4 * part;
+        for (int jl = threadIdx.x >> 3; jl < cols; jl += 32) {
+          float4* ge = reinterpret_cast<float4*>(grow + (int64_t)jl * C);
+          float4* se = reinterpret_cast<float4*>(srow + jl * kPitch);
+          if (STORE)
+            *ge = *se;
+          else
+            *se = *ge;
+        }
+      }
     }
   } else if (layout) {  // NHWC, odd channel count: line = (il, jl), lane = c'
     if (lane >= g.ncg) return;
-    for (int cell = warp; cell < rows * cols; cell += nwarps) {
-      const int il = cell / cols, jl = cell - il * cols;
-      float* ge = gptr + (((int64_t)g.b * h_out + i_first + il) * w_out + j_first + jl) * C + g.c0 + lane;
-      float* se = s_out + (il * cols_pitch + jl) * kPitch + lane;
-      if (STORE)
-        *ge = *se;
-      else
-        *se = *ge;
-    }
+    for (int il = 0; il < rows; ++il)
+      for (int jl = warp; jl < cols; jl += nwarps) {
+        float* ge = gptr + (((int64_t)g.b * h_out + i_first + il) * w_out + j_first + jl) * C + g.c0 + lane;
+        float* se = s_out + (il * cols_pitch + jl) * kPitch + lane;
+        if (STORE)
+          *ge = *se;
+        else
+          *se = *ge;
+      }
   } else {  // NCHW: line = (c', il), lanes = columns
-    for (int line = warp; line < g.ncg * rows; line += nwarps) {
-      const int cl = line / rows, il = line - cl * rows;
+    for (int cl = warp; cl < g.ncg; cl += nwarps)
+      for (int il = 0; il < rows; ++il)
       for (int jl = lane; jl < cols; jl += 32) {
         float* ge = gptr + (((int64_t)g.b * C + g.c0 + cl) * h_out + i_first + il) * w_out + j_first + jl;
         float* se = s_out + (il * cols_pitch + jl) * kPitch + cl;
@@ -327,7 +334,6 @@ __device__ __forceinline__ void tile_transfer(const TileGeom& g, float* s_out, f
         else
           *se = *ge;
       }
-    }
   }
 }
 
@@ -340,6 +346,20 @@ __device__ __forceinline__ uint32_t line_row_bits(const TileGeom& g, const TileS
   return (t.rowmask[cl] >> (ha - g.h_lo)) & ((1u << (hb - ha)) - 1u);
 }
 
+// The lines whose windows can hold a voxel, collected so that ALL warps share them: a voxel occupies one scrambled
+// channel, so the non-empty lines of a tile belong to a few c' -- with one warp per c' most warps idled at the barrier.
+// `*t.n_lines` must be zero on entry; every thread of the CTA calls this.
+__device__ __forceinline__ void collect_lines(const TileGeom& g, const TileSmem& t, int H, int pk, int ps, int pp) {
+  {
+    const int cl = threadIdx.x >> 3, il = threadIdx.x & 7;
+    if (cl < g.ncg && il < g.nib && line_row_bits(g, t, cl, g.i0 + il, H, pk, ps, pp))
+      t.lines[atomicAdd(t.n_lines, 1)] = (unsigned short)((cl << 8) | il);
+  }
+  if (g.nib > 8 && threadIdx.x < g.ncg && line_row_bits(g, t, threadIdx.x, g.i0 + 8, H, pk, ps, pp))  // the halo's 9th row
+    t.lines[atomicAdd(t.n_lines, 1)] = (unsigned short)((threadIdx.x << 8) | 8);
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
     k_bev_pool_fwd(const float* __restrict__ feats, const int* __restrict__ next, const int* __restrict__ pixmap,
                    const uint32_t* __restrict__ rowbits, int C, int H, int W, int h_out, int w_out, int pk, int ps,
@@ -350,6 +370,8 @@ __global__ void __launch_bounds__(256)
   t.heads = reinterpret_cast<int*>(t.out + kIB * kJC * kPitch);
   t.plo = t.heads + pairs_cap * max_pix;
   t.rowmask = reinterpret_cast<uint32_t*>(t.plo + pairs_cap);
+  t.n_lines = reinterpret_cast<int*>(t.rowmask + kCG);
+  t.lines = reinterpret_cast<unsigned short*>(t.n_lines + 1);
   t.list = nullptr;
   t.arg = nullptr;
   const TileGeom g = tile_geom(C, H, W, h_out, w_out, pk, ps, pp);
@@ -357,20 +379,19 @@ __global__ void __launch_bounds__(256)
     float4* o4 = reinterpret_cast<float4*>(t.out);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int u = threadIdx.x; u < kIB * kJC * kPitch / 4; u += blockDim.x) o4[u] = z;
+    if (threadIdx.x == 0) *t.n_lines = 0;
   }
   if (tile_lookup<false>(g, t, C, H, W, max_pix, pixmap, rowbits)) {
-    // a warp takes the non-empty (c', i) lines of its channels, lane = column: the 32 windows of a line share their
+    collect_lines(g, t, H, pk, ps, pp);
+    // a warp takes one non-empty (c', i) line at a time, lane = column: the 32 windows of a line share their
     // scrambled rows and neighbouring lanes read neighbouring cells
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int cl = warp; cl < g.ncg; cl += 8) {
-      if (!t.rowmask[cl]) continue;
-      for (int il = 0; il < g.nib; ++il) {
-        if (!line_row_bits(g, t, cl, g.i0 + il, H, pk, ps, pp)) continue;
-        if (lane < g.njc)
-          t.out[(il * kJC + lane) * kPitch + cl] = window_scan<false>(g, t, cl, g.i0 + il, g.j0 + lane, C, H, W, pk, ps, pp,
-                                                                      max_pix, policy, feats, next, nullptr, nullptr,
-                                                                      nullptr);
-      }
+    const int n_lines = *t.n_lines;
+    for (int e = warp; e < n_lines; e += 8) {
+      const int cl = t.lines[e] >> 8, il = t.lines[e] & 255;
+      if (lane < g.njc)
+        t.out[(il * kJC + lane) * kPitch + cl] = window_scan<false>(g, t, cl, g.i0 + il, g.j0 + lane, C, H, W, pk, ps, pp,
+                                                                    max_pix, policy, feats, next, nullptr, nullptr, nullptr);
     }
     __syncthreads();
   }
@@ -393,8 +414,10 @@ __global__ void __launch_bounds__(256)
   t.heads = reinterpret_cast<int*>(t.out + kIBh * kJCh * kPitch);
   t.plo = t.heads + pairs_cap * max_pix;
   t.rowmask = reinterpret_cast<uint32_t*>(t.plo + pairs_cap);
-  t.list = reinterpret_cast<int*>(t.rowmask + kCG) + 1;  // list[-1] = number of entries
+  t.n_lines = reinterpret_cast<int*>(t.rowmask + kCG);
+  t.list = t.n_lines + 2;  // list[-1] = number of entries
   t.arg = reinterpret_cast<unsigned char*>(t.list + pairs_cap * max_pix);
+  t.lines = reinterpret_cast<unsigned short*>(t.arg + kCG * kIBh * kJCh);
   const TileGeom own = tile_geom(C, H, W, h_out, w_out, pk, ps, pp);
   TileGeom g = own;  // windows handled = owned + halo
   g.i0 = max(own.i0 - 1, 0);
@@ -403,26 +426,24 @@ __global__ void __launch_bounds__(256)
   g.njc = own.j0 + own.njc - g.j0;
   if (g.j0 < own.j0) g.jbits |= 1u << (own.jt - 1);  // the halo column's cells lie in the previous block's range
   cell_region(g, H, W, pk, ps, pp);
-  if (threadIdx.x == 0) t.list[-1] = 0;
+  if (threadIdx.x == 0) t.list[-1] = 0, *t.n_lines = 0;
   __syncthreads();
   if (!tile_lookup<true>(g, t, C, H, W, max_pix, pixmap, rowbits)) return;
+  collect_lines(g, t, H, pk, ps, pp);
   static_assert((kCG * kIBh * kJCh) % 4 == 0, "winning-cell table is filled word-wise");
   for (int u = threadIdx.x; u < kCG * kIBh * kJCh / 4; u += blockDim.x) reinterpret_cast<uint32_t*>(t.arg)[u] = 0xffffffffu;
   tile_transfer<false>(g, t.out, const_cast<float*>(grad_out), layout, C, h_out, w_out, g.i0, g.j0, g.nib, g.njc, kJCh);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // phase A: winning cell of every window of the non-empty lines
-  for (int cl = warp; cl < g.ncg; cl += 8) {
-    if (!t.rowmask[cl]) continue;
-    for (int il = 0; il < g.nib; ++il) {
-      if (!line_row_bits(g, t, cl, g.i0 + il, H, pk, ps, pp)) continue;
-      for (int jl = lane; jl < g.njc; jl += 32) {
-        if (t.out[(il * kJCh + jl) * kPitch + cl] == 0.f) continue;  // a zero gradient adds nothing
-        int row = -1, ch = 0, pos = 255;
-        window_scan<true>(g, t, cl, g.i0 + il, g.j0 + jl, C, H, W, pk, ps, pp, max_pix, policy, feats, next, &row, &ch,
-                          &pos);
-        if (row != -1) t.arg[(cl * kIBh + il) * kJCh + jl] = (unsigned char)pos;
-      }
+  // phase A: winning cell of every window of the non-empty lines (shared by all warps)
+  const int n_lines = *t.n_lines;
+  for (int e = warp; e < n_lines; e += 8) {
+    const int cl = t.lines[e] >> 8, il = t.lines[e] & 255;
+    for (int jl = lane; jl < g.njc; jl += 32) {
+      if (t.out[(il * kJCh + jl) * kPitch + cl] == 0.f) continue;  // a zero gradient adds nothing
+      int row = -1, ch = 0, pos = 255;
+      window_scan<true>(g, t, cl, g.i0 + il, g.j0 + jl, C, H, W, pk, ps, pp, max_pix, policy, feats, next, &row, &ch, &pos);
+      if (row != -1) t.arg[(cl * kIBh + il) * kJCh + jl] = (unsigned char)pos;
     }
   }
   __syncthreads();
@@ -488,13 +509,14 @@ static int bev_max_pix(int C, int pk, int ps, int cols) { return ((cols - 1) * p
 static int bev_pairs_cap(int C, int pk, int ps, int rows) { return (C < kCG ? C : kCG) * ((rows - 1) * ps + pk); }
 static size_t bev_smem_fwd(int C, int pk, int ps) {  // staged tile + heads + first pixels + row masks
   const size_t pairs = bev_pairs_cap(C, pk, ps, kIB);
-  return sizeof(float) * kIB * kJC * kPitch + sizeof(int) * pairs * (bev_max_pix(C, pk, ps, kJC) + 1) + sizeof(int) * kCG + 16;
+  return sizeof(float) * kIB * kJC * kPitch + sizeof(int) * pairs * (bev_max_pix(C, pk, ps, kJC) + 1) + sizeof(int) * kCG +
+         sizeof(int) + 2 * kCG * kIB + 16;
 }
 static size_t bev_smem_bwd(int C, int pk, int ps) {  // + halo, occupied-entry list, winning cells
   const size_t pairs = bev_pairs_cap(C, pk, ps, kIBh);
   const size_t mp = bev_max_pix(C, pk, ps, kJCh);
-  return sizeof(float) * kIBh * kJCh * kPitch + sizeof(int) * pairs * (mp + 1) + sizeof(int) * kCG + sizeof(int) * (pairs * mp + 1) +
-         (size_t)kCG * kIBh * kJCh + 32;
+  return sizeof(float) * kIBh * kJCh * kPitch + sizeof(int) * pairs * (mp + 1) + sizeof(int) * kCG + sizeof(int) * (pairs * mp + 2) +
+         (size_t)kCG * kIBh * kJCh + 2 * kCG * kIBh + 32;
 }
 static int64_t bev_tiles(int B, int C, int h_out, int w_out) {
   return (int64_t)B * ceil_div(C, kCG) * ceil_div(h_out, kIB) * ceil_div(w_out, kJC);

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kBnThreads)
 #pragma unroll 4
     for (int64_t r = g.r0 + g.ry; r < g.r1; r += g.rpp) {
       const int64_t i = r * (C >> 2) + g.cq;
-      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + r * dy_ld4 + g.cq),
+      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + (dy_ld4 == (C >> 2) ? i : r * dy_ld4 + g.cq)),
                                relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z, relu);
       const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
       const float4 d = make_float4(v.x - mu.x, v.y - mu.y, v.z - mu.z, v.w - mu.w);

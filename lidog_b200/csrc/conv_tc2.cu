@@ -757,6 +757,7 @@ struct Wgrad2Args {
   const uint16_t* dY;
   float* partial;  // [chunks][K][Cin][Cout]
   int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np, bmax;
+  int na_max;  // 32-channel sub-blocks per A stage = min(4, Cin / 32): a 96-channel layer stages 24 KB, not 32 KB
   int64_t n_tiles;
   int* err;
 };
@@ -772,7 +773,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
   const int m0 = mb * 128;
   const int na = min(4, (g.Cin - m0) / 32);  // real 32-channel sub-blocks of the A operand
   const int nb = g.Cout / 32;
-  const int stageA = 4 * kSub, stageB = nb * kSub;
+  // (the MMA always reads 4 sub-blocks = 128 accumulator lanes; lanes of sub-blocks that are not staged hold whatever
+  // the neighbouring stage holds and are never read back: the epilogue stops at Cin)
+  const int stageA = g.na_max * kSub, stageB = nb * kSub;
   uint8_t* smA = smem;
   uint8_t* smB = smem + (size_t)g.sa * stageA;
   uint8_t* smI = smB + (size_t)g.sb * stageB;  // id ring: ni slots of 128 row ids
@@ -872,18 +875,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     }
   } else if (warp == kBWarp) {
     // ---------------------------------------------------------------- dY producer (one warp, whole tiles)
+    // ncu (profiles/r02_a_wgrad2_source_stalls.txt): the MMA warp polled this ring 41 times per tile -- two stages and
+    // two dependent global latencies per tile (out_row, then the rows) could not keep it fed.  The row ids of the NEXT
+    // tile are now loaded before the wait for a free stage, and the ring is as deep as shared memory allows.
     int bs = 0;
     uint32_t bphase = 0;
     const int lim = (int)g.plan.n_out;
-    for (int64_t tile = t0; tile < t1; tile += tstep) {
-      if (!group_mask(tile)) continue;
-      int rows[16];
+    auto next_tile = [&](int64_t t) {
+      while (t < t1 && !group_mask(t)) t += tstep;
+      return t;
+    };
+    auto load_rows = [&](int (&rows)[16], int64_t tile) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int sl = (int)(tile * LG_TILE_ROWS) + 8 * i + (lane >> 2);
         const int r = g.plan.out_row ? __ldg(g.plan.out_row + sl) : sl;
         rows[i] = (r < lim) ? r : -1;
       }
+    };
+    int64_t tile = next_tile(t0);
+    int rows[16], rows_n[16];
+    if (tile < t1) load_rows(rows, tile);
+    while (tile < t1) {
+      const int64_t nxt = next_tile(tile + tstep);
+      if (nxt < t1) load_rows(rows_n, nxt);
       if (lane == 0) mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 12);
       __syncwarp();
       uint8_t* dst = smB + (size_t)bs * stageB;
@@ -894,6 +909,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
         bs = 0;
         bphase ^= 1;
       }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rows[i] = rows_n[i];
+      tile = nxt;
     }
   } else if (warp == kMmaWarp) {
     // warp-uniform loop, one elected lane issues (see k_gemm2)
@@ -1037,15 +1055,15 @@ int debug_profile(long long* out16, int reset) {
 //   LIDOG_G2_SB / LIDOG_G2_PC   pin the panel-ring depth / 32-channel chunks per operand stage
 //   LIDOG_G2_RING    0 = the ring shape of the first validated lean kernel (32 id slots, 3 weight stages when they fit)
 //   LIDOG_G2_T       pin the tiles per super-tile (parity tests sweep the multi-tile schedules on small inputs)
-//   LIDOG_WG_CTAS / LIDOG_WG_BATCH   wgrad CTA target / MMA-warp batch
+//   LIDOG_WG_CTAS / LIDOG_WG_BATCH / LIDOG_WG_SB   wgrad CTA target / MMA-warp batch / dY ring depth
 struct Switches {
-  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2;
+  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb;
 };
 static const Switches& switches() {
   static const Switches sw = {env_int("LIDOG_DBG", 0),     env_int("LIDOG_ACC_SETS", 2), env_int("LIDOG_G2_OPT", 3),
                               env_int("LIDOG_G2_SB", 0),   env_int("LIDOG_G2_PC", 0),    env_int("LIDOG_G2_RING", 1) != 0,
                               env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
-                              env_int("LIDOG_G2_MMA2", 0)};
+                              env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0)};
   return sw;
 }
 
@@ -1271,9 +1289,12 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
   g.n_tiles = plan->n_slots / LG_TILE_ROWS;
   g.err = err;
-  const size_t stageA = 4 * (size_t)kSub, stageB = (size_t)(Cout / 32) * kSub;
-  g.sb = 2;
-  g.sa = 5;
+  g.na_max = Cin / 32 < 4 ? Cin / 32 : 4;
+  const size_t stageA = (size_t)g.na_max * kSub, stageB = (size_t)(Cout / 32) * kSub;
+  // dY ring: 3 stages when 4 X stages still fit next to them (the MMA warp waited on this ring, see the dY producer)
+  g.sb = (4 * stageA + 3 * stageB + wgrad_tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
+  if (switches().wg_sb >= 2) g.sb = switches().wg_sb;
+  g.sa = 6;
   while (g.sa > 2 && g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
   {

@@ -92,17 +92,22 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
         const int km = K - 1 - k;
         if (r >= 0) {  // the mirror pair: voxel r sees o through offset K-1-k
           nbr[(int64_t)km * n_slots + r] = (int32_t)o;
-          atomicOr(&tile_mask[(int64_t)(r / LG_TILE_ROWS) * mask_words + (km >> 5)], 1u << (km & 31));
-          if (row_mask) atomicOr(&row_mask[r], 1u << (km & 31));
+          if (row_mask) {
+            atomicOr(&row_mask[r], 1u << (km & 31));  // (mask-sorted plans rebuild the tile masks after the sort)
+          } else {
+            // one atomic per distinct tile of the warp's hits: consecutive voxels mostly hit consecutive rows
+            const int tile = r / LG_TILE_ROWS;
+            const unsigned peers = __match_any_sync(__activemask(), tile);
+            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+              atomicOr(&tile_mask[(int64_t)tile * mask_words + (km >> 5)], 1u << (km & 31));
+          }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, r >= 0);
         if (bal) wmask[k >> 5] |= 1u << (k & 31);
         if (row_mask) {
           rmask |= (r >= 0 ? 1u : 0u) << (k & 31);
-          if (bal && (threadIdx.x & 31) == 0) {
-            atomicAdd(&k_count[k], (unsigned)__popc(bal));
-            atomicAdd(&k_count[km], (unsigned)__popc(bal));
-          }
+          // (k_count of the mirror offset equals this one: k_sort_keys reads count[min(k, K-1-k)])
+          if (bal && (threadIdx.x & 31) == 0) atomicAdd(&k_count[k], (unsigned)__popc(bal));
         }
       }
   // centre offset: the voxel itself
@@ -125,13 +130,17 @@ __global__ void __launch_bounds__(LG_TILE_ROWS)
     atomicOr(&tile_mask[(int64_t)blockIdx.x * mask_words + threadIdx.x], s_mask[threadIdx.x]);
 }
 
+static bool neighbors_symmetric(int same_set, int kernel_size) {
+  static const int sym_on = env_int("LIDOG_KMAP_SYM", 1);
+  return same_set && sym_on && (kernel_size & 1) && kernel_size >= 3;
+}
+
 static int launch_neighbors(const void* table_in, int64_t capacity_in, const int32_t* out_coords4, int64_t n_out,
                             int kernel_size, int offset_scale, int row_offset, int same_set, int K, int words,
                             int32_t* nbr, int64_t n_slots, uint32_t* tile_mask, uint32_t* row_mask,
                             unsigned int* k_count, cudaStream_t stream) {
   const unsigned grid = (unsigned)(n_slots / LG_TILE_ROWS);
-  static const int sym_on = env_int("LIDOG_KMAP_SYM", 1);
-  if (same_set && sym_on && (kernel_size & 1) && kernel_size >= 3) {
+  if (neighbors_symmetric(same_set, kernel_size)) {
     const int half = K / 2;
     LG_CUDA_OK(cudaMemsetAsync(nbr + (int64_t)(half + 1) * n_slots, 0xFF, sizeof(int32_t) * (size_t)half * n_slots, stream));
     LG_CUDA_OK(cudaMemsetAsync(tile_mask, 0, sizeof(uint32_t) * (size_t)grid * words, stream));
@@ -230,15 +239,17 @@ __global__ void k_up2_layout(const int* k_start, int64_t n, int* k_slot_base, ui
 // significant: rows that own an unusual neighbour end up together, so far fewer (tile, offset)
 // units carry mostly-empty rows (measured on kitti-shaped scans: 0.29 -> 0.69 of the gathered rows real).
 __global__ void k_sort_keys(const uint32_t* __restrict__ row_mask, const unsigned int* __restrict__ k_count, int K,
-                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                            int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals, int sym_counts) {
   __shared__ int s_pos[32];
+  // sym_counts: only the first half of the offsets was counted (k_neighbors_sym); count[k] = count[K-1-k]
+  auto cnt = [&](int k) { return k_count[sym_counts ? min(k, K - 1 - k) : k]; };
   if (threadIdx.x < 32) {
     const int k = threadIdx.x;
     int rank = 0;  // number of offsets rarer than k
     if (k < K) {
-      const unsigned ck = k_count[k];
+      const unsigned ck = cnt(k);
       for (int j = 0; j < K; ++j) {
-        const unsigned cj = k_count[j];
+        const unsigned cj = cnt(j);
         rank += (cj < ck || (cj == ck && j < k)) ? 1 : 0;
       }
     }
@@ -358,8 +369,8 @@ extern "C" int lg_kernel_map_sorted(const void* table_in, int64_t capacity_in, c
   int rc = launch_neighbors(table_in, capacity_in, out_coords4, n_out, kernel_size, offset_scale, in_row_offset, same_set,
                             K, 1, w.nbr_nat, n_slots, w.nat_tile_mask, w.row_mask, w.k_count, stream);
   if (rc) return rc;
-  k_sort_keys<<<(unsigned)ceil_div(n_out, 256), 256, 0, stream>>>(w.row_mask, w.k_count, K, n_out, w.keys_in,
-                                                                  w.vals_in);
+  k_sort_keys<<<(unsigned)ceil_div(n_out, 256), 256, 0, stream>>>(w.row_mask, w.k_count, K, n_out, w.keys_in, w.vals_in,
+                                                                  neighbors_symmetric(same_set, kernel_size) ? 1 : 0);
   LG_LAUNCH_OK();
   size_t cub_bytes = w.cub_bytes;
   LG_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, (const uint32_t*)w.keys_in, w.keys_out,
