@@ -328,6 +328,20 @@ size_t lg_peer_exchange_bytes(void);
 int lg_peer_sum(const double* local, int32_t n, void* const* peer_bufs, int32_t world, int32_t rank, uint64_t epoch,
                 double* out, void* stream);
 
+/* ------------------------------------------------------------------ LiDOG's DICE criteria
+ *
+ * soft = 0: DICELoss(ignore_label) -- the BEV criterion (utils/losses/losses.py:56-97; trainer_lighting_2d.py:181);
+ * soft = 1: SoftDICELoss(ignore_label, eps, is_kitti) -- the 3D criterion (:129-187, soft targets :100-126;
+ *           trainer_lighting_2d.py:194; is_kitti when num_classes == 19, :97-98).
+ * logits float [n, C] (C <= 32), target int64 [n].  Forward: loss (device float) and coef float[2C] for the backward.
+ * Backward: dlogits [n, C] = grad_scale[0] (device float, nullable = 1) * dLoss/dlogits.  Two HBM passes each way
+ * instead of the reference's CPU round trip; fixed-order reductions. */
+int lg_dice_forward(const float* logits, const int64_t* target, int64_t n, int32_t C, int32_t ignore_label,
+                    int32_t soft, float eps, int32_t is_kitti, float* loss, float* coef, void* stream);
+int lg_dice_backward(const float* logits, const int64_t* target, int64_t n, int32_t C, int32_t ignore_label,
+                     int32_t soft, float eps, int32_t is_kitti, const float* coef, const float* grad_scale,
+                     float* dlogits, void* stream);
+
 /* ------------------------------------------------------------------ BEV projection */
 
 size_t lg_bev_workspace(int64_t n, int32_t C, int32_t batch_size, int32_t H, int32_t W);

@@ -96,6 +96,8 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _i32, _vp]),
     "lg_peer_exchange_bytes": (_sz, []),
     "lg_peer_sum": (C.c_int, [_vp, _i32, C.POINTER(C.c_void_p), _i32, _i32, C.c_uint64, _vp, _vp]),
+    "lg_dice_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
+    "lg_dice_backward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp]),
     "lg_bev_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "lg_bev_forward": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _vp]),
@@ -114,7 +116,7 @@ KERNELS_PER_CALL = {
     "lg_bev_forward": 2, "lg_bev_backward": 3,
     "lg_bn_stats": 2, "lg_bn_finalize": 1, "lg_bn_apply": 1, "lg_bn_bwd_stats": 2, "lg_bn_bwd_finalize": 1,
     "lg_bn_bwd_gscale": 1, "lg_bn_bwd_apply": 1, "lg_peer_sum": 1,
-    "lg_bn_layer_backward": 3,
+    "lg_bn_layer_backward": 3, "lg_dice_forward": 2, "lg_dice_backward": 1,
 }
 COUNTS: dict = {}
 _RAW = None

@@ -141,7 +141,7 @@ constexpr int kCG = 32;   // scrambled channels per CTA
 constexpr int kIB = 8;    // output rows per CTA
 constexpr int kJC = 32;   // output columns per CTA
 constexpr int kPitch = kCG + 4;  // floats per staged (i, j) cell group: float4-aligned, conflict-free 128-bit reads
-constexpr int kIBh = kIB + 1, kJCh = kJC + 1;  // backward: windows including the halo row above / column left
+constexpr int kIBh = kIB + 1;  // backward: window rows including the halo row above
 
 struct TileGeom {
   int b, c0, i0, j0;  // sample, first scrambled channel, first window row / column handled
@@ -185,7 +185,7 @@ struct TileSmem {
   unsigned short* lines;  // non-empty (c', i) lines of the tile: (cl << 8) | il; *n_lines = their count
   int* n_lines;
   int* list;          // backward: occupied (pair, pixel) entries of the tile; list[-1] = their count
-  unsigned char* arg; // backward: [kCG][kIBh][kJCh] winning cell of every window (position in the window, 255 = none)
+  unsigned char* arg; // backward: [kCG][kIBh][kJC] winning cell of every window (position in the window, 255 = none)
 };
 
 // Phase 1.  Returns false (uniformly) when no pixel of the tile is occupied.  One coalesced rowbits load per
@@ -403,6 +403,17 @@ __global__ void __launch_bounds__(256)
 // LAST window (largest i, j) containing a cell sums the cell's windows in ascending (i, j) order -- for that it also
 // scans the windows one row above and one column left of its own (halo).  Every gradient element is written by
 // exactly one thread with a fixed summation order: no atomics, bit-reproducible, and equal to torch's CPU backward.
+// A tile owns kIB x kJB = 8 x 31 windows, so that owned + halo columns fill exactly one warp (a 33rd column made every
+// line cost two passes); the window gradients are read from global memory only for the windows a cell actually won
+// (no staged copy of the gradient tile: 43 KB of shared memory and 10 % of the instructions in the first version).
+constexpr int kJB = kJC - 1;  // owned window columns of a backward tile
+
+__device__ __forceinline__ float grad_at(const float* __restrict__ grad_out, int layout, int b, int c, int i, int j, int C,
+                                         int h_out, int w_out) {
+  return __ldg(grad_out + (layout ? (((int64_t)b * h_out + i) * w_out + j) * C + c
+                                  : (((int64_t)b * C + c) * h_out + i) * w_out + j));
+}
+
 __global__ void __launch_bounds__(256)
     k_bev_pool_bwd(const float* __restrict__ feats, const int* __restrict__ next, const int* __restrict__ pixmap,
                    const uint32_t* __restrict__ rowbits, int C, int H, int W, int h_out, int w_out, int pk, int ps,
@@ -410,40 +421,59 @@ __global__ void __launch_bounds__(256)
                    float* __restrict__ grad_feats) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   TileSmem t;
-  t.out = reinterpret_cast<float*>(s_dyn);
-  t.heads = reinterpret_cast<int*>(t.out + kIBh * kJCh * kPitch);
+  t.out = nullptr;
+  t.heads = reinterpret_cast<int*>(s_dyn);
   t.plo = t.heads + pairs_cap * max_pix;
   t.rowmask = reinterpret_cast<uint32_t*>(t.plo + pairs_cap);
   t.n_lines = reinterpret_cast<int*>(t.rowmask + kCG);
   t.list = t.n_lines + 2;  // list[-1] = number of entries
   t.arg = reinterpret_cast<unsigned char*>(t.list + pairs_cap * max_pix);
-  t.lines = reinterpret_cast<unsigned short*>(t.arg + kCG * kIBh * kJCh);
-  const TileGeom own = tile_geom(C, H, W, h_out, w_out, pk, ps, pp);
+  t.lines = reinterpret_cast<unsigned short*>(t.arg + kCG * kIBh * kJC);
+  // owned windows
+  TileGeom own;
+  {
+    const int n_jb = (w_out + kJB - 1) / kJB, n_ib = (h_out + kIB - 1) / kIB, n_cg = (C + kCG - 1) / kCG;
+    int idx = blockIdx.x;
+    own.jt = idx % n_jb;
+    own.j0 = own.jt * kJB;
+    idx /= n_jb;
+    own.i0 = (idx % n_ib) * kIB;
+    idx /= n_ib;
+    own.c0 = (idx % n_cg) * kCG;
+    own.b = idx / n_cg;
+    own.ncg = min(kCG, C - own.c0);
+    own.nib = min(kIB, h_out - own.i0);
+    own.njc = min(kJB, w_out - own.j0);
+  }
   TileGeom g = own;  // windows handled = owned + halo
   g.i0 = max(own.i0 - 1, 0);
   g.j0 = max(own.j0 - 1, 0);
   g.nib = own.i0 + own.nib - g.i0;
   g.njc = own.j0 + own.njc - g.j0;
-  if (g.j0 < own.j0) g.jbits |= 1u << (own.jt - 1);  // the halo column's cells lie in the previous block's range
   cell_region(g, H, W, pk, ps, pp);
+  {  // occupancy bits of the forward's column blocks (kJC windows wide) that overlap this tile's cell columns
+    const int bw = kJC * ps, cover = (kJC - 1) * ps + pk, n_jc = (w_out + kJC - 1) / kJC;
+    int lo = g.w_lo + pp - cover + 1;
+    lo = lo <= 0 ? 0 : (lo + bw - 1) / bw;
+    const int hi = min(n_jc - 1, (g.w_hi - 1 + pp) / bw);
+    g.jbits = (hi - lo == 31) ? 0xffffffffu : (((1u << (hi - lo + 1)) - 1u) << lo);
+  }
   if (threadIdx.x == 0) t.list[-1] = 0, *t.n_lines = 0;
   __syncthreads();
   if (!tile_lookup<true>(g, t, C, H, W, max_pix, pixmap, rowbits)) return;
-  collect_lines(g, t, H, pk, ps, pp);
-  static_assert((kCG * kIBh * kJCh) % 4 == 0, "winning-cell table is filled word-wise");
-  for (int u = threadIdx.x; u < kCG * kIBh * kJCh / 4; u += blockDim.x) reinterpret_cast<uint32_t*>(t.arg)[u] = 0xffffffffu;
-  tile_transfer<false>(g, t.out, const_cast<float*>(grad_out), layout, C, h_out, w_out, g.i0, g.j0, g.nib, g.njc, kJCh);
-  __syncthreads();
+  static_assert((kCG * kIBh * kJC) % 4 == 0, "winning-cell table is filled word-wise");
+  for (int u = threadIdx.x; u < kCG * kIBh * kJC / 4; u += blockDim.x) reinterpret_cast<uint32_t*>(t.arg)[u] = 0xffffffffu;
+  collect_lines(g, t, H, pk, ps, pp);  // (ends with a barrier: the table above is complete too)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // phase A: winning cell of every window of the non-empty lines (shared by all warps)
+  // phase A: winning cell of every window of the non-empty lines (shared by all warps); lane = window column
   const int n_lines = *t.n_lines;
   for (int e = warp; e < n_lines; e += 8) {
     const int cl = t.lines[e] >> 8, il = t.lines[e] & 255;
-    for (int jl = lane; jl < g.njc; jl += 32) {
-      if (t.out[(il * kJCh + jl) * kPitch + cl] == 0.f) continue;  // a zero gradient adds nothing
+    if (lane < g.njc) {
       int row = -1, ch = 0, pos = 255;
-      window_scan<true>(g, t, cl, g.i0 + il, g.j0 + jl, C, H, W, pk, ps, pp, max_pix, policy, feats, next, &row, &ch, &pos);
-      if (row != -1) t.arg[(cl * kIBh + il) * kJCh + jl] = (unsigned char)pos;
+      window_scan<true>(g, t, cl, g.i0 + il, g.j0 + lane, C, H, W, pk, ps, pp, max_pix, policy, feats, next, &row, &ch,
+                        &pos);
+      if (row != -1) t.arg[(cl * kIBh + il) * kJC + lane] = (unsigned char)pos;
     }
   }
   __syncthreads();
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(256)
     const int m_row = ((g.c0 + cl) * H + h) * W;
     const int p = t.plo[q] + d;
     const int m_a = max(p * C, m_row + g.w_lo), m_b = min(p * C + C, m_row + g.w_hi);
-    int i_hi = min((h + pp) / ps, h_out - 1);
+    const int i_hi = min((h + pp) / ps, h_out - 1);
     if (h > i_hi * ps - pp + pk - 1) continue;  // below the last window: the cell is pooled by nobody
     if (i_hi < own.i0 || i_hi >= own.i0 + own.nib) continue;  // another tile owns this row of cells
     const int i_lo = max((h + pp - pk + ps) / ps, 0);
@@ -473,9 +503,8 @@ __global__ void __launch_bounds__(256)
       for (int i = i_lo; i <= i_hi; ++i)
         for (int j = j_lo; j <= j_hi; ++j) {
           const int pos = (h - (i * ps - pp)) * pk + (w - (j * ps - pp));
-          const int il = i - g.i0, jl = j - g.j0;
-          if (t.arg[(cl * kIBh + il) * kJCh + jl] == pos) {
-            sum += t.out[(il * kJCh + jl) * kPitch + cl];
+          if (t.arg[(cl * kIBh + (i - g.i0)) * kJC + (j - g.j0)] == pos) {
+            sum += grad_at(grad_out, layout, g.b, g.c0 + cl, i, j, C, h_out, w_out);
             hit = true;
           }
         }
@@ -512,14 +541,14 @@ static size_t bev_smem_fwd(int C, int pk, int ps) {  // staged tile + heads + fi
   return sizeof(float) * kIB * kJC * kPitch + sizeof(int) * pairs * (bev_max_pix(C, pk, ps, kJC) + 1) + sizeof(int) * kCG +
          sizeof(int) + 2 * kCG * kIB + 16;
 }
-static size_t bev_smem_bwd(int C, int pk, int ps) {  // + halo, occupied-entry list, winning cells
+static size_t bev_smem_bwd(int C, int pk, int ps) {  // heads + first pixels + masks + occupied-entry list + winning cells
   const size_t pairs = bev_pairs_cap(C, pk, ps, kIBh);
-  const size_t mp = bev_max_pix(C, pk, ps, kJCh);
-  return sizeof(float) * kIBh * kJCh * kPitch + sizeof(int) * pairs * (mp + 1) + sizeof(int) * kCG + sizeof(int) * (pairs * mp + 2) +
-         (size_t)kCG * kIBh * kJCh + 2 * kCG * kIBh + 32;
+  const size_t mp = bev_max_pix(C, pk, ps, kJC);
+  return sizeof(int) * pairs * (mp + 1) + sizeof(int) * kCG + sizeof(int) * (pairs * mp + 2) + (size_t)kCG * kIBh * kJC +
+         2 * kCG * kIBh + 32;
 }
-static int64_t bev_tiles(int B, int C, int h_out, int w_out) {
-  return (int64_t)B * ceil_div(C, kCG) * ceil_div(h_out, kIB) * ceil_div(w_out, kJC);
+static int64_t bev_tiles(int B, int C, int h_out, int w_out, int cols = kJC) {
+  return (int64_t)B * ceil_div(C, kCG) * ceil_div(h_out, kIB) * ceil_div(w_out, cols);
 }
 
 static int bev_check(int64_t n, int C, int B, int H, int W, int pk, int ps, int pp, int policy, const char* who) {
@@ -589,16 +618,15 @@ extern "C" int lg_bev_backward(const int32_t* coords4, const float* feats, int64
   LG_CHECK_ARG(workspace && workspace_bytes >= w.total, "lg_bev_backward: workspace too small");
   if (n == 0) return LG_OK;
   LG_CHECK_ARG(feats && grad_out && grad_feats, "lg_bev_backward: null pointer");
-  LG_CHECK_ARG(((uintptr_t)grad_out & 15) == 0, "lg_bev_backward: grad_out must be 16-byte aligned");
   const int h_out = (H + 2 * pp - pk) / ps + 1, w_out = (W + 2 * pp - pk) / ps + 1;
   LG_CHECK_ARG(layout == 0 || layout == 1, "lg_bev_backward: layout must be 0 (NCHW) or 1 (NHWC)");
   LG_CUDA_OK(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)n * C, stream));
   const size_t smem = bev_smem_bwd(C, pk, ps);
-  const int64_t blocks = bev_tiles(batch_size, C, h_out, w_out);
+  const int64_t blocks = bev_tiles(batch_size, C, h_out, w_out, kJB);
   LG_CHECK_ARG(blocks < ((int64_t)1 << 31), "lg_bev_backward: too many output tiles");
   LG_CUDA_OK(cudaFuncSetAttribute(k_bev_pool_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bev_pool_bwd<<<(unsigned)blocks, 256, smem, stream>>>(feats, w.next, w.pixmap, w.rowbits, C, H, W, h_out, w_out, pk,
-                                                          ps, pp, policy, layout, bev_max_pix(C, pk, ps, kJCh),
+                                                          ps, pp, policy, layout, bev_max_pix(C, pk, ps, kJC),
                                                           bev_pairs_cap(C, pk, ps, kIBh), grad_out, grad_feats);
   LG_LAUNCH_OK();
   if (policy == LG_BEV_LAST) {

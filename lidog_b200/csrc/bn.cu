@@ -735,15 +735,18 @@ static int peer_ctx(const lgPeerCtx* p, PeerCtx* out, int extra_epoch, const cha
   return LG_OK;
 }
 
+constexpr int kTailSlicesMax = 128;
+// slices of ~32 partial rows: the epilogue statistics of a 648 k-row layer are 20 k partial rows, and with 32 slices
+// every thread of the tail walked ~80 of them one after the other (12 us per layer, profiles/r02_a_launch_summary.txt)
 static int tail_slices(int64_t n_partials) {
-  int64_t s = (n_partials + 63) / 64;
-  return (int)(s < 1 ? 1 : (s > 32 ? 32 : s));
+  int64_t s = (n_partials + 31) / 32;
+  return (int)(s < 1 ? 1 : (s > kTailSlicesMax ? kTailSlicesMax : s));
 }
 
 static size_t fwd_scratch(int64_t n, int C, int64_t n_stat_rows) {
   size_t b = 0;
   if (!n_stat_rows) b += arena_pad(sizeof(float) * (size_t)kBnMaxBlocks * 2 * C);
-  b += arena_pad(sizeof(double) * 32 * 2 * C) + arena_pad(sizeof(double) * (2 * C + 1));
+  b += arena_pad(sizeof(double) * kTailSlicesMax * 2 * C) + arena_pad(sizeof(double) * (2 * C + 1));
   return b;
 }
 
@@ -766,7 +769,7 @@ static int bn_branch_forward(const lgBnBranch* b, int64_t n, int C, ArenaCursor*
   t.C = C;
   t.n_local = (double)n;
   const int S = tail_slices(n_partials);
-  t.slices = (double*)arena_take(ar, sizeof(double) * 32 * 2 * C);
+  t.slices = (double*)arena_take(ar, sizeof(double) * kTailSlicesMax * 2 * C);
   t.sums = (double*)arena_take(ar, sizeof(double) * (2 * C + 1));
   t.gamma = b->gamma, t.beta = b->beta, t.eps = b->eps, t.momentum = b->momentum;
   t.running_mean = b->running_mean, t.running_var = b->running_var, t.nbt = (long long*)b->num_batches_tracked;
@@ -834,7 +837,7 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   if (rc) return rc;
   ArenaCursor ar;
   rc = arena_begin(stream,
-                   arena_pad(sizeof(float) * (size_t)kBnMaxBlocks * 6 * C) + arena_pad(sizeof(double) * 32 * 6 * C) +
+                   arena_pad(sizeof(float) * (size_t)kBnMaxBlocks * 6 * C) + arena_pad(sizeof(double) * kTailSlicesMax * 6 * C) +
                        arena_pad(sizeof(double) * 6 * C) + arena_pad(sizeof(float) * 3 * C) +
                        2 * arena_pad(sizeof(float) * 3 * C),
                    &ar);
@@ -851,7 +854,7 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   t.C = C;
   t.n_branches = b ? 2 : 1;
   t.want_gscale = 0;  // the residual gradient feeds an elementwise backward, never a 16-bit convolution operand
-  t.slices = (double*)arena_take(&ar, sizeof(double) * 32 * 6 * C);
+  t.slices = (double*)arena_take(&ar, sizeof(double) * kTailSlicesMax * 6 * C);
   t.sums = (double*)arena_take(&ar, sizeof(double) * 6 * C);
   t.maxes = (float*)arena_take(&ar, sizeof(float) * 3 * C);
   const lgBnBwdBranch* brs[2] = {a, b};

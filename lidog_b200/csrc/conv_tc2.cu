@@ -1057,13 +1057,14 @@ int debug_profile(long long* out16, int reset) {
 //   LIDOG_G2_T       pin the tiles per super-tile (parity tests sweep the multi-tile schedules on small inputs)
 //   LIDOG_WG_CTAS / LIDOG_WG_BATCH / LIDOG_WG_SB   wgrad CTA target / MMA-warp batch / dY ring depth
 struct Switches {
-  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb;
+  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb, wg_na4, wg_sa;
 };
 static const Switches& switches() {
   static const Switches sw = {env_int("LIDOG_DBG", 0),     env_int("LIDOG_ACC_SETS", 2), env_int("LIDOG_G2_OPT", 3),
                               env_int("LIDOG_G2_SB", 0),   env_int("LIDOG_G2_PC", 0),    env_int("LIDOG_G2_RING", 1) != 0,
                               env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
-                              env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0)};
+                              env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0),
+                              env_int("LIDOG_WG_NA4", 0),  env_int("LIDOG_WG_SA", 0)};
   return sw;
 }
 
@@ -1290,11 +1291,12 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   g.n_tiles = plan->n_slots / LG_TILE_ROWS;
   g.err = err;
   g.na_max = Cin / 32 < 4 ? Cin / 32 : 4;
+  if (switches().wg_na4) g.na_max = 4;  // LIDOG_WG_NA4=1: the 4-sub-block stages of round 1 (bisecting switch)
   const size_t stageA = (size_t)g.na_max * kSub, stageB = (size_t)(Cout / 32) * kSub;
   // dY ring: 3 stages when 4 X stages still fit next to them (the MMA warp waited on this ring, see the dY producer)
   g.sb = (4 * stageA + 3 * stageB + wgrad_tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
   if (switches().wg_sb >= 2) g.sb = switches().wg_sb;
-  g.sa = 6;
+  g.sa = switches().wg_sa >= 2 ? switches().wg_sa : 6;
   while (g.sa > 2 && g.sa * stageA + g.sb * stageB + wgrad_tail_bytes(g.sa, g.sb) > kSmemBudget) --g.sa;
   g.np = g.sa < kProdWarps ? g.sa : kProdWarps;
   {

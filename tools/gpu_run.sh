@@ -47,6 +47,7 @@ for step in "$@"; do
               python tools/ncu_summary.py ${O}_ncu_bev.ncu-rep > ${O}_ncu_bev.txt; ncu -i ${O}_ncu_bev.ncu-rep --page source --csv > ${O}_ncu_bev_source.csv 2>/dev/null
               ls -la ${O}_ncu_bev*; rm -f ${O}_ncu_bev.ncu-rep ;;
     sanitize) bash tools/sanitize.sh ${O} ;;
+    bisect)   bash tools/bisect_wgrad.sh 2>&1 | tee ${O}_bisect.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
