@@ -220,6 +220,7 @@ __device__ __forceinline__ float4 masked(float4 dy, float4 y, int relu) {
 }
 
 // partial row of a block: [sum g | sum g*(x-mean) | sum g*(x2-mean2) | max|g| | max|x-mean| | max|x2-mean2|] x C
+template <bool DENSE>
 __global__ void __launch_bounds__(kBnThreads)
     k_bn_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                    const float* __restrict__ st, const float* __restrict__ x2, const float* __restrict__ st2, int relu,
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kBnThreads)
 #pragma unroll 4
     for (int64_t r = g.r0 + g.ry; r < g.r1; r += g.rpp) {
       const int64_t i = r * (C >> 2) + g.cq;
-      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + (dy_ld4 == (C >> 2) ? i : r * dy_ld4 + g.cq)),
+      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + (DENSE ? i : r * dy_ld4 + g.cq)),
                                relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z, relu);
       const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
       const float4 d = make_float4(v.x - mu.x, v.y - mu.y, v.z - mu.z, v.w - mu.w);
@@ -670,7 +671,7 @@ extern "C" int lg_bn_bwd_stats(const float* dy, const float* y, const float* x, 
   LG_CHECK_ARG(workspace && workspace_bytes >= lg_bn_workspace(n, C), "lg_bn_bwd_stats: workspace too small");
   const int nb = bn_blocks(n);
   float* partial = (float*)workspace;
-  k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
+  k_bn_bwd_stats<true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
   LG_LAUNCH_OK();
   k_bn_bwd_reduce<<<ceil_div(6 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>(partial, nb, C, sums, maxes);
   LG_LAUNCH_OK();
@@ -735,7 +736,7 @@ static int peer_ctx(const lgPeerCtx* p, PeerCtx* out, int extra_epoch, const cha
   return LG_OK;
 }
 
-constexpr int kTailSlicesMax = 128;
+constexpr int kTailSlicesMax = 64;
 // slices of ~32 partial rows: the epilogue statistics of a 648 k-row layer are 20 k partial rows, and with 32 slices
 // every thread of the tail walked ~80 of them one after the other (12 us per layer, profiles/r02_a_launch_summary.txt)
 static int tail_slices(int64_t n_partials) {
@@ -844,8 +845,12 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   if (rc) return rc;
   const int nb = bn_blocks(n);
   float* partial = (float*)arena_take(&ar, sizeof(float) * (size_t)kBnMaxBlocks * 6 * C);
-  k_bn_bwd_stats<<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
-                                                          b ? b->stats : nullptr, relu, n, C, partial, dy_ld >> 2);
+  if (dy_ld == C)
+    k_bn_bwd_stats<true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
+                                                                  b ? b->stats : nullptr, relu, n, C, partial, C >> 2);
+  else
+    k_bn_bwd_stats<false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
+                                                                   b ? b->stats : nullptr, relu, n, C, partial, dy_ld >> 2);
   LG_LAUNCH_OK();
   BnBwdTail t;
   memset(&t, 0, sizeof(t));

@@ -209,6 +209,8 @@ struct Gemm2Args {
   const float* out_scale;
   const float* bias;
   int Ck, N, n_blk, flip, umma_fmt;
+  int accum;  // Y += result instead of Y = result: the gradient of a tensor with several consumers (residual branch +
+              // convolution, convolution + downsample convolution) is summed in the epilogue, not by a separate pass
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs, 16 = no proxy fence,
             // 32 = no result stores, 64 = no row-id copies, 128 = stage release by plain arrive (only with 4);
             // 8 = per-role cycle counters of CTA 0
@@ -623,8 +625,8 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
           // row [sum | sum of squares] per tile; a fixed shuffle order and a fixed (tile, warp) slot keep the later
           // reduction deterministic although tiles are handed out dynamically.
           float* strow = g.stats ? g.stats + ((tile0 + t) * kEpiWarps + warp) * 2 * (int64_t)g.N + n0 : nullptr;
-          if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
-            if (row_ok)
+          if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros (nothing to add when accumulating)
+            if (row_ok && !g.accum)
               for (int n = 0; n < g.n_blk; n += 4) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
@@ -675,8 +677,14 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
               for (int j = 0; j < 8; ++j) {
                 const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
                 if (srow[j] >= 0) {
+                  float4* dst = reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7));
+                  float4 w = o;
+                  if (g.accum) {
+                    const float4 old = *dst;
+                    w.x += old.x, w.y += old.y, w.z += old.z, w.w += old.w;
+                  }
                   if (!(dbg & 32))  // dbg 32: experiment without the result stores
-                    *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
+                    *dst = w;
                   cs.x += o.x, cs.y += o.y, cs.z += o.z, cs.w += o.w;
                   cq.x = fmaf(o.x, o.x, cq.x), cq.y = fmaf(o.y, o.y, cq.y), cq.z = fmaf(o.z, o.z, cq.z),
                   cq.w = fmaf(o.w, o.w, cq.w);
@@ -712,6 +720,10 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
                   if (g.bias) {
                     const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
                     o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+                  }
+                  if (g.accum) {
+                    const float4 old = *reinterpret_cast<const float4*>(yrow + n + 4 * q);
+                    o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                   }
                   *reinterpret_cast<float4*>(yrow + n + 4 * q) = o;
                 }
@@ -757,7 +769,7 @@ struct Wgrad2Args {
   const uint16_t* dY;
   float* partial;  // [chunks][K][Cin][Cout]
   int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np, bmax;
-  int na_max;  // 32-channel sub-blocks per A stage = min(4, Cin / 32): a 96-channel layer stages 24 KB, not 32 KB
+  int na_max;  // 32-channel sub-blocks per A stage (4; see the launcher for why not min(4, Cin / 32))
   int64_t n_tiles;
   int* err;
 };
@@ -1064,13 +1076,13 @@ static const Switches& switches() {
                               env_int("LIDOG_G2_SB", 0),   env_int("LIDOG_G2_PC", 0),    env_int("LIDOG_G2_RING", 1) != 0,
                               env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
                               env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0),
-                              env_int("LIDOG_WG_NA4", 0),  env_int("LIDOG_WG_SA", 0)};
+                              env_int("LIDOG_WG_NA4", 1),  env_int("LIDOG_WG_SA", 0)};
   return sw;
 }
 
 // host launcher: forward / dgrad
 int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void* B16, int N, int flip_k, int fmt,
-                    const float* out_scale, const float* bias, float* Y, float* stats, cudaStream_t stream) {
+                    const float* out_scale, const float* bias, float* Y, float* stats, int accum, cudaStream_t stream) {
   using namespace v2;
   const Switches& sw = switches();
   int sm_count = 0;
@@ -1082,6 +1094,7 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   g.A = (const uint16_t*)A16;
   g.Y = Y;
   g.stats = stats;
+  g.accum = accum;
   g.out_scale = out_scale;
   g.bias = bias;
   g.Ck = Ck;
@@ -1290,8 +1303,11 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   g.umma_fmt = (fmt == LG_FMT_BF16) ? 1 : 0;
   g.n_tiles = plan->n_slots / LG_TILE_ROWS;
   g.err = err;
-  g.na_max = Cin / 32 < 4 ? Cin / 32 : 4;
-  if (switches().wg_na4) g.na_max = 4;  // LIDOG_WG_NA4=1: the 4-sub-block stages of round 1 (bisecting switch)
+  // An X stage always holds 4 sub-blocks (32 KB) although a 96-channel layer fills 3 and a 32-channel layer 1.
+  // Packing the stages tighter (LIDOG_WG_NA4=0) is WRONG: the M = 128 MMA then reads its unused sub-blocks out of
+  // the neighbouring stages, and the full-scale parity test (tests/test_gpu_fullscale.py) measured 0.3-2.5 % error in
+  // dW -- bisected on hardware (profiles/r02_b_wgrad_bisect.log); the switch stays for that record only.
+  g.na_max = switches().wg_na4 ? 4 : (Cin / 32 < 4 ? Cin / 32 : 4);
   const size_t stageA = (size_t)g.na_max * kSub, stageB = (size_t)(Cout / 32) * kSub;
   // dY ring: 3 stages when 4 X stages still fit next to them (the MMA warp waited on this ring, see the dY producer)
   g.sb = (4 * stageA + 3 * stageB + wgrad_tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
@@ -1375,7 +1391,7 @@ extern "C" int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t 
               "tools/legacy/conv_tc_gen1.cu as the record)", gather_mode);
     return LG_ERR_UNSUPPORTED;
   }
-  return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, nullptr, (cudaStream_t)stream_);
+  return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, nullptr, 0, (cudaStream_t)stream_);
 }
 
 extern "C" size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin, int32_t Cout) {
@@ -1408,13 +1424,14 @@ extern "C" int lg_conv_layer_forward(const lgConvPlan* plan, const void* X16, in
     rc = lg_prep_weights(W, plan->kernel_volume, Cin, Cout, w16, w16t, fmt, stream_);
     if (rc) return rc;
   }
-  return launch_gemm_tc2(plan, X16, Cin, w16t, Cout, 0, fmt, nullptr, bias, Y, stat_partials, (cudaStream_t)stream_);
+  return launch_gemm_tc2(plan, X16, Cin, w16t, Cout, 0, fmt, nullptr, bias, Y, stat_partials, 0, (cudaStream_t)stream_);
 }
 
 /* dgrad and wgrad of one MinkowskiConvolution in one host call; the split-K partials live in the library arena. */
 extern "C" int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConvPlan* plan_wgrad, int32_t flip_dgrad,
                                       const void* X16, int32_t Cin, const void* dY16, int32_t Cout, const void* w16,
-                                      int32_t fmt, const float* inv_scale, float* dX, float* dW, void* stream_) {
+                                      int32_t fmt, const float* inv_scale, float* dX, int32_t accumulate_dx, float* dW,
+                                      void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc;
   LG_CHECK_ARG(dY16, "lg_conv_layer_backward: null gradient");
@@ -1422,7 +1439,8 @@ extern "C" int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConv
     rc = check_gemm(plan_dgrad, Cout, Cin, fmt, "lg_conv_layer_backward(dgrad)");
     if (rc) return rc;
     LG_CHECK_ARG(w16, "lg_conv_layer_backward: null weights");
-    rc = launch_gemm_tc2(plan_dgrad, dY16, Cout, w16, Cin, flip_dgrad, fmt, inv_scale, nullptr, dX, nullptr, stream);
+    rc = launch_gemm_tc2(plan_dgrad, dY16, Cout, w16, Cin, flip_dgrad, fmt, inv_scale, nullptr, dX, nullptr,
+                         accumulate_dx ? 1 : 0, stream);
     if (rc) return rc;
   }
   if (dW) {

@@ -46,6 +46,16 @@ for step in "$@"; do
                 -k regex:'k_bev_' -c 4 -o ${O}_ncu_bev -f python bench.py --ncu > ${O}_ncu5.log 2>&1
               python tools/ncu_summary.py ${O}_ncu_bev.ncu-rep > ${O}_ncu_bev.txt; ncu -i ${O}_ncu_bev.ncu-rep --page source --csv > ${O}_ncu_bev_source.csv 2>/dev/null
               ls -la ${O}_ncu_bev*; rm -f ${O}_ncu_bev.ncu-rep ;;
+    syncbn)   NG=${NG:-$(nvidia-smi -L | wc -l)}
+              timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29531 \
+                tools/syncbn_check.py 2>&1 | grep -E "syncbn|SYNCBN|Error|error" | tail -5 | tee ${O}_syncbn${NG}.log ;;
+    bench_ddp|bench_ddp_nuscenes|bench_ddp_mix3d)
+              NG=${NG:-$(nvidia-smi -L | wc -l)}
+              case $step in bench_ddp) A="--shape kitti --batch 8";; bench_ddp_nuscenes) A="--shape nuscenes --batch 16";; *) A="--shape mix3d --batch 8";; esac
+              timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29532 \
+                bench.py --gpus $NG --steps 8 --warmup 3 $A > ${O}_${step}_${NG}gpu.json 2> ${O}_${step}_${NG}gpu.err
+              tail -1 ${O}_${step}_${NG}gpu.err | cut -c1-200; cut -c1-400 ${O}_${step}_${NG}gpu.json ;;
+    tests_syncbn) timeout 900 python -m pytest tests/test_gpu_syncbn.py -m gpu -q 2>&1 | tail -5 | tee ${O}_tests_syncbn.log ;;
     sanitize) bash tools/sanitize.sh ${O} ;;
     bisect)   bash tools/bisect_wgrad.sh 2>&1 | tee ${O}_bisect.log ;;
     *) echo "unknown step $step" ;;
