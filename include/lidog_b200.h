@@ -218,13 +218,11 @@ int lg_conv_wgrad_tc(const lgConvPlan* plan, const void* X16, int32_t Cin, const
 int lg_conv_layer_forward(const lgConvPlan* plan, const void* X16, int32_t Cin, const float* W, int32_t Cout, void* w16,
                           void* w16t, int32_t prep, int32_t fmt, const float* bias, float* Y, float* stat_partials,
                           void* stream);
-/* Backward: dX = inv_scale * dgrad (skipped when dX is NULL; dX += ... when accumulate_dx != 0: the gradient of a
- * tensor that also feeds a residual branch or a second convolution is summed in the epilogue instead of by a separate
- * pass), dW = inv_scale * wgrad (skipped when dW is NULL); dY16 is the 16-bit gradient scaled by 1 / inv_scale[0]
- * (inv_scale nullable).  Split-K partials: library arena. */
+/* Backward: dX = inv_scale * dgrad (skipped when dX is NULL), dW = inv_scale * wgrad (skipped when dW is NULL);
+ * dY16 is the 16-bit gradient scaled by 1 / inv_scale[0] (inv_scale nullable).  Split-K partials: library arena. */
 int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConvPlan* plan_wgrad, int32_t flip_dgrad,
                            const void* X16, int32_t Cin, const void* dY16, int32_t Cout, const void* w16, int32_t fmt,
-                           const float* inv_scale, float* dX, int32_t accumulate_dx, float* dW, void* stream);
+                           const float* inv_scale, float* dX, float* dW, void* stream);
 
 /* Library-owned scratch arena (one block per device and stream, outside any caching allocator): bytes currently held,
  * and release (synchronises).  The layer-level calls size it themselves. */

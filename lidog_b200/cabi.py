@@ -78,7 +78,7 @@ SIGNATURES = {
     "lg_conv_wgrad_tc_workspace": (_sz, [_PP, _i32, _i32]),
     "lg_conv_wgrad_tc": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "lg_conv_layer_forward": (C.c_int, [_PP, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "lg_conv_layer_backward": (C.c_int, [_PP, _PP, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "lg_conv_layer_backward": (C.c_int, [_PP, _PP, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "lg_arena_bytes": (_sz, []),
     "lg_arena_release": (C.c_int, []),
     "lg_debug_profile": (C.c_int, [_vp, C.c_int]),

@@ -209,8 +209,6 @@ struct Gemm2Args {
   const float* out_scale;
   const float* bias;
   int Ck, N, n_blk, flip, umma_fmt;
-  int accum;  // Y += result instead of Y = result: the gradient of a tensor with several consumers (residual branch +
-              // convolution, convolution + downsample convolution) is summed in the epilogue, not by a separate pass
   int dbg;  // experiment switches (LIDOG_DBG): 1 = no B loads, 2 = no A copies, 4 = no MMAs, 16 = no proxy fence,
             // 32 = no result stores, 64 = no row-id copies, 128 = stage release by plain arrive (only with 4);
             // 8 = per-role cycle counters of CTA 0
@@ -625,8 +623,8 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
           // row [sum | sum of squares] per tile; a fixed shuffle order and a fixed (tile, warp) slot keep the later
           // reduction deterministic although tiles are handed out dynamically.
           float* strow = g.stats ? g.stats + ((tile0 + t) * kEpiWarps + warp) * 2 * (int64_t)g.N + n0 : nullptr;
-          if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros (nothing to add when accumulating)
-            if (row_ok && !g.accum)
+          if (!((am >> t) & 1u)) {  // no neighbour at all: bias / zeros
+            if (row_ok)
               for (int n = 0; n < g.n_blk; n += 4) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g.bias) o = *reinterpret_cast<const float4*>(g.bias + n0 + n);
@@ -677,14 +675,12 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
               for (int j = 0; j < 8; ++j) {
                 const float4 o = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * j) * kStgPitch + 4 * (lane & 7));
                 if (srow[j] >= 0) {
-                  float4* dst = reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7));
-                  float4 w = o;
-                  if (g.accum) {
-                    const float4 old = *dst;
-                    w.x += old.x, w.y += old.y, w.z += old.z, w.w += old.w;
-                  }
+                  // (Summing the gradient of a multi-consumer tensor here -- read-modify-write instead of a store --
+                  // was measured: the 31 separate adds it removes cost 0.6 ms per step, the loads in this epilogue
+                  // 2.8 ms (k_gemm2 8.39 -> 11.17 ms, profiles/r02_c_launch_summary_grad_accum_experiment.txt): the
+                  // accumulators drain late and the MMA warp stalls.  Not kept.)
                   if (!(dbg & 32))  // dbg 32: experiment without the result stores
-                    *dst = w;
+                    *reinterpret_cast<float4*>(g.Y + (int64_t)srow[j] * g.N + n0 + n + 4 * (lane & 7)) = o;
                   cs.x += o.x, cs.y += o.y, cs.z += o.z, cs.w += o.w;
                   cq.x = fmaf(o.x, o.x, cq.x), cq.y = fmaf(o.y, o.y, cq.y), cq.z = fmaf(o.z, o.z, cq.z),
                   cq.w = fmaf(o.w, o.w, cq.w);
@@ -720,10 +716,6 @@ __global__ void __launch_bounds__(kThreadsG2, 1) k_gemm2(const Gemm2Args g, cons
                   if (g.bias) {
                     const float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + n + 4 * q);
                     o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
-                  }
-                  if (g.accum) {
-                    const float4 old = *reinterpret_cast<const float4*>(yrow + n + 4 * q);
-                    o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                   }
                   *reinterpret_cast<float4*>(yrow + n + 4 * q) = o;
                 }
@@ -1082,7 +1074,7 @@ static const Switches& switches() {
 
 // host launcher: forward / dgrad
 int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void* B16, int N, int flip_k, int fmt,
-                    const float* out_scale, const float* bias, float* Y, float* stats, int accum, cudaStream_t stream) {
+                    const float* out_scale, const float* bias, float* Y, float* stats, cudaStream_t stream) {
   using namespace v2;
   const Switches& sw = switches();
   int sm_count = 0;
@@ -1094,7 +1086,6 @@ int launch_gemm_tc2(const lgConvPlan* plan, const void* A16, int Ck, const void*
   g.A = (const uint16_t*)A16;
   g.Y = Y;
   g.stats = stats;
-  g.accum = accum;
   g.out_scale = out_scale;
   g.bias = bias;
   g.Ck = Ck;
@@ -1391,7 +1382,7 @@ extern "C" int lg_conv_gemm_tc(const lgConvPlan* plan, const void* A16, int32_t 
               "tools/legacy/conv_tc_gen1.cu as the record)", gather_mode);
     return LG_ERR_UNSUPPORTED;
   }
-  return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, nullptr, 0, (cudaStream_t)stream_);
+  return launch_gemm_tc2(plan, A16, Ck, B16, N, flip_k, fmt, out_scale, bias, Y, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" size_t lg_conv_wgrad_tc_workspace(const lgConvPlan* plan, int32_t Cin, int32_t Cout) {
@@ -1424,14 +1415,13 @@ extern "C" int lg_conv_layer_forward(const lgConvPlan* plan, const void* X16, in
     rc = lg_prep_weights(W, plan->kernel_volume, Cin, Cout, w16, w16t, fmt, stream_);
     if (rc) return rc;
   }
-  return launch_gemm_tc2(plan, X16, Cin, w16t, Cout, 0, fmt, nullptr, bias, Y, stat_partials, 0, (cudaStream_t)stream_);
+  return launch_gemm_tc2(plan, X16, Cin, w16t, Cout, 0, fmt, nullptr, bias, Y, stat_partials, (cudaStream_t)stream_);
 }
 
 /* dgrad and wgrad of one MinkowskiConvolution in one host call; the split-K partials live in the library arena. */
 extern "C" int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConvPlan* plan_wgrad, int32_t flip_dgrad,
                                       const void* X16, int32_t Cin, const void* dY16, int32_t Cout, const void* w16,
-                                      int32_t fmt, const float* inv_scale, float* dX, int32_t accumulate_dx, float* dW,
-                                      void* stream_) {
+                                      int32_t fmt, const float* inv_scale, float* dX, float* dW, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc;
   LG_CHECK_ARG(dY16, "lg_conv_layer_backward: null gradient");
@@ -1439,8 +1429,7 @@ extern "C" int lg_conv_layer_backward(const lgConvPlan* plan_dgrad, const lgConv
     rc = check_gemm(plan_dgrad, Cout, Cin, fmt, "lg_conv_layer_backward(dgrad)");
     if (rc) return rc;
     LG_CHECK_ARG(w16, "lg_conv_layer_backward: null weights");
-    rc = launch_gemm_tc2(plan_dgrad, dY16, Cout, w16, Cin, flip_dgrad, fmt, inv_scale, nullptr, dX, nullptr,
-                         accumulate_dx ? 1 : 0, stream);
+    rc = launch_gemm_tc2(plan_dgrad, dY16, Cout, w16, Cin, flip_dgrad, fmt, inv_scale, nullptr, dX, nullptr, stream);
     if (rc) return rc;
   }
   if (dW) {

@@ -15,7 +15,6 @@ import torch
 import torch.nn as nn
 
 from .. import cabi
-from . import _gradacc
 from ._grad16 import take_grad16
 from .sparse_tensor import SparseTensor
 
@@ -137,7 +136,6 @@ class SparseConvFunction(torch.autograd.Function):
             K, (cin, cout) = 1, kernel.shape
         x = x.contiguous()
         ctx.plans, ctx.shape, ctx.kdim = plans, (K, cin, cout), kernel.dim()
-        ctx.x_key = (x.data_ptr(), tuple(x.shape))
         ctx.has_bias = bias is not None
         ctx.tc = _tc_ok(cin, cout) and x.shape[0] > 0
         L = cabi.lib()
@@ -203,22 +201,13 @@ class SparseConvFunction(torch.autograd.Function):
             inv_ptr = None if scale is None else scale.data_ptr() + 4  # scale = {2^k, 2^-k, ...}
             want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             if CONFIG["layer_calls"] and not PROFILE["enabled"]:
-                target = None
                 if want_dx:
-                    # another consumer of x already produced its gradient: add into it (me/_gradacc.py)
-                    target = _gradacc.take(ctx.x_key[0], ctx.x_key[1])
-                    dx = target if target is not None else torch.empty((p_dgrad.n_out, cin), dtype=torch.float32,
-                                                                       device=dy.device)
+                    dx = torch.empty((p_dgrad.n_out, cin), dtype=torch.float32, device=dy.device)
                 if want_dw:
                     dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dy.device)
                 cabi.check(L.lg_conv_layer_backward(p_dgrad.cref, p_wgrad.cref, flip, x16.data_ptr(), cin,
                                                     dy16.data_ptr(), cout, w16.data_ptr(), fmt, inv_ptr, cabi.ptr(dx),
-                                                    1 if target is not None else 0, cabi.ptr(dw), cabi.stream_of(dy)),
-                           "lg_conv_layer_backward")
-                if want_dx:
-                    _gradacc.offer(ctx.x_key[0], dx)  # a further consumer of x may add into the same tensor
-                    if target is not None:
-                        dx = None  # autograd already holds `target`; this node contributes nothing separately
+                                                    cabi.ptr(dw), cabi.stream_of(dy)), "lg_conv_layer_backward")
                 cabi.count_launches("lg_conv_layer_backward", (1 if want_dx else 0) + (2 if want_dw else 0))
             else:
                 inv = None if scale is None else scale[1:]

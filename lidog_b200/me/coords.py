@@ -15,7 +15,7 @@ import time
 import torch
 
 from .. import cabi
-from . import _grad16, _gradacc
+from . import _grad16
 
 
 def _check_count(count_status: torch.Tensor, what: str) -> int:
@@ -157,7 +157,6 @@ def _round_up(a, b):
 class CoordinateManager:
     def __init__(self, coordinates: torch.Tensor):
         _grad16.clear()  # a new batch: no gradient of the previous one is still wanted
-        _gradacc.clear()
         self.device = coordinates.device
         self._adopt(build_levels(coordinates), coordinates.shape[0])
 
@@ -179,7 +178,6 @@ class CoordinateManager:
         index (no second hash build for ME.SparseTensor).  `res` = the level list of `build_levels`, or the dict of a
         single `coords_unique` call."""
         _grad16.clear()
-        _gradacc.clear()
         self = cls.__new__(cls)
         levels = res["levels"] if isinstance(res, dict) and "levels" in res else ([res] if isinstance(res, dict) else res)
         self.device = levels[0]["coords"].device

@@ -37,7 +37,6 @@ CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1")),
           "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1"))}
 C_byref = _C.byref
 
-from . import _gradacc
 from ._grad16 import publish_grad16
 
 
@@ -145,7 +144,6 @@ class FusedBNFunction(torch.autograd.Function):
         box["y16"], box["fmt"] = y16, fmt
         ctx.save_for_backward(x, x2, y if relu else None, st_a, st_b, w, w2)
         ctx.meta = (relu, res is not None, fmt, ex)
-        ctx.res_key = None if res is None else res.data_ptr()
         return y
 
     @staticmethod
@@ -181,8 +179,6 @@ class FusedBNFunction(torch.autograd.Function):
                                           cabi.peer_ctx(ex, 1), cabi.stream_of(x)), "lg_bn_layer_backward")
         dw, db = dgb[0], dgb[1]
         dw2 = db2 = None
-        if dres is not None:  # the residual tensor usually also feeds the block's first convolution
-            _gradacc.offer(ctx.res_key, dres)
         if use16:
             publish_grad16(dx, dx16, scales, fmt)
         if x2 is not None:
