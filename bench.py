@@ -48,6 +48,12 @@ def parse():
     p.add_argument("--empty-cache", action="store_true",
                    help="call torch.cuda.empty_cache() before every step, as the reference loop does "
                         "(trainer_lighting_2d.py:147-148, clear_cache_int: 1)")
+    p.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("LIDOG_NCCL_CTAS", "4")),
+                   help="upper bound on the CTAs NCCL's all-reduce kernels may occupy (0 = NCCL's default).  The gradient "
+                        "all-reduce overlaps the backward pass; the sparse-conv kernels are persistent, one CTA per SM, so "
+                        "every SM NCCL holds is an SM they lose for the whole overlap, and 154 MB over NVLink 5 need few")
+    p.add_argument("--ddp-bucket-mb", type=int, default=int(os.environ.get("LIDOG_DDP_BUCKET_MB", "25")),
+                   help="DistributedDataParallel bucket_cap_mb (25 = torch default)")
     p.add_argument("--ncu", action="store_true",
                    help="profiling run: 1 warm-up + 1 step between cudaProfilerStart/Stop, no e2e / CPU legs "
                         "(use with ncu --profile-from-start off; numbers printed under ncu are not bench values)")
@@ -221,7 +227,16 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if args.nccl_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = args.nccl_ctas
+                opts.config.min_ctas = 1
+            except Exception:
+                opts = None
+                os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     cabi.lib()
     torch.backends.cudnn.benchmark = True  # train_lidog.py:312
 
@@ -234,7 +249,8 @@ def run_ours(args):
     if world > 1:  # train_lidog.py:227-231
         net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
         # gradient_as_bucket_view: the all-reduce works on the gradient storage itself (no bucket copies); same result
-        ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+        ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=args.ddp_bucket_mb)
     else:
         ddp = net
     trainer = step.LidogTrainer(ddp, num_classes=args.classes, shape=args.shape)
@@ -380,6 +396,8 @@ def run_ours(args):
                            "parallelism": f"dp{world}" + ((" (DDP gradient all-reduce over NCCL; SyncBN exchange: " +
                                                            ("in-kernel over NVLink peer memory" if mepeer.active()
                                                             else "NCCL all_reduce") + ")") if world > 1 else ""),
+                           "nccl_max_ctas": args.nccl_ctas if world > 1 else None,
+                           "ddp_bucket_cap_mb": args.ddp_bucket_mb if world > 1 else None,
                            "empty_cache_every_step": bool(args.empty_cache),
                            "arena_bytes": int(cabi.lib().lg_arena_bytes()),
                            "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",

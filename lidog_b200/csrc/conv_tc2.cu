@@ -762,11 +762,14 @@ struct Wgrad2Args {
   float* partial;  // [chunks][K][Cin][Cout]
   int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np, bmax;
   int na_max;  // 32-channel sub-blocks per A stage (4; see the launcher for why not min(4, Cin / 32))
+  int dbg;     // DBG instantiation only (LIDOG_WG_DBG): 1 = no dY gathers, 2 = no X gathers, 4 = no MMAs, 8 = no partial stores
   int64_t n_tiles;
   int* err;
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
+  const int dbg = DBG ? g.dbg : 0;  // experiment switches fold away in the production instantiation
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -863,7 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
             mbar_wait(&emptyA[stage], phase ^ 1, g.err, 11);
           }
           __syncwarp();
-          gather_stage(smA + (size_t)stage * stageA, g.X, g.Cin, m0, na, rows, lane);
+          if (!(dbg & 2)) gather_stage(smA + (size_t)stage * stageA, g.X, g.Cin, m0, na, rows, lane);
           cp_async_arrive_noinc(&fullA[stage]);
         }
         turn = (turn + 1 == g.np) ? 0 : turn + 1;
@@ -906,8 +909,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
       if (lane == 0) mbar_wait(&emptyB[bs], bphase ^ 1, g.err, 12);
       __syncwarp();
       uint8_t* dst = smB + (size_t)bs * stageB;
-      for (int c0 = 0; c0 < nb; c0 += 4)
-        gather_stage(dst + c0 * kSub, g.dY, g.Cout, c0 * 32, min(4, nb - c0), rows, lane);
+      if (!(dbg & 1))
+        for (int c0 = 0; c0 < nb; c0 += 4)
+          gather_stage(dst + c0 * kSub, g.dY, g.Cout, c0 * 32, min(4, nb - c0), rows, lane);
       cp_async_arrive_noinc(&fullB[bs]);
       if (++bs == g.sb) {
         bs = 0;
@@ -963,10 +967,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
             const uint64_t da0 = desc_hi | (uint64_t)(a_base + s * a_stage16);
             const uint32_t d_tmem = tmem_base + j * g.Cout;
             const uint32_t acc0 = (started >> j) & 1u;
-            umma_f16(d_tmem, da0, db0, idesc, acc0);
+            if (!(dbg & 4)) {
+              umma_f16(d_tmem, da0, db0, idesc, acc0);
 #pragma unroll
-            for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
-              umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
+              for (int q = 1; q < LG_TILE_ROWS / 16; ++q)  // K = 16 gathered rows per MMA
+                umma_f16(d_tmem, da0 + q * (16 * kRowB >> 4), db0 + q * (16 * kRowB >> 4), idesc, 1u);
+            }
             umma_commit(&emptyA[s]);
             if (++s == g.sa) s = 0;
           }
@@ -1015,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = 0u;
         }
-        if (ci < g.Cin) {
+        if (ci < g.Cin && !(dbg & 8)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<float4*>(prow + n + 4 * q) =
@@ -1061,14 +1067,15 @@ int debug_profile(long long* out16, int reset) {
 //   LIDOG_G2_T       pin the tiles per super-tile (parity tests sweep the multi-tile schedules on small inputs)
 //   LIDOG_WG_CTAS / LIDOG_WG_BATCH / LIDOG_WG_SB   wgrad CTA target / MMA-warp batch / dY ring depth
 struct Switches {
-  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb, wg_na4, wg_sa;
+  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb, wg_na4, wg_sa, wg_dbg;
 };
 static const Switches& switches() {
   static const Switches sw = {env_int("LIDOG_DBG", 0),     env_int("LIDOG_ACC_SETS", 2), env_int("LIDOG_G2_OPT", 3),
                               env_int("LIDOG_G2_SB", 0),   env_int("LIDOG_G2_PC", 0),    env_int("LIDOG_G2_RING", 1) != 0,
                               env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
                               env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0),
-                              env_int("LIDOG_WG_NA4", 1),  env_int("LIDOG_WG_SA", 0)};
+                              env_int("LIDOG_WG_NA4", 1),  env_int("LIDOG_WG_SA", 0),
+                              env_int("LIDOG_WG_DBG", 0)};
   return sw;
 }
 
@@ -1315,9 +1322,15 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
     set_error("lg_conv_wgrad_tc: shared memory %zu exceeds the budget (Cin=%d Cout=%d)", smem, Cin, Cout);
     return LG_ERR_UNSUPPORTED;
   }
-  LG_CUDA_OK(cudaFuncSetAttribute(k_wgrad2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(g.n_groups * g.m_blocks), (unsigned)chunks);
-  k_wgrad2<<<grid, kThreads, smem, stream>>>(g);
+  g.dbg = switches().wg_dbg;
+  if (g.dbg) {
+    LG_CUDA_OK(cudaFuncSetAttribute(k_wgrad2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad2<true><<<grid, kThreads, smem, stream>>>(g);
+  } else {
+    LG_CUDA_OK(cudaFuncSetAttribute(k_wgrad2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad2<false><<<grid, kThreads, smem, stream>>>(g);
+  }
   LG_LAUNCH_OK();
   return launch_reduce_partials((const float*)workspace, chunks, (int64_t)plan->kernel_volume * Cin * Cout, out_scale,
                                 dW, stream);

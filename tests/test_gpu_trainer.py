@@ -3,8 +3,11 @@ against the same step on the CPU oracle: batched voxelisation, BEV label image, 
 losses, backward, Adam.  Inputs: a batch of two small scans -- one nuScenes-shaped crop and one Mix3D-shaped
 merge (two crops re-quantised through float32 metres, utils/datasets/mix3D.py:43-87).
 
-Tolerances: integer products of the data path bit exact; losses within 2e-3 (fp32 SIMT convolutions) / 3e-2 (fp16
-tensor-core operands, 63 layers deep); parameter gradients within 20x that, layer by layer.
+Tolerances (about twice the measured values, profiles/r02_*_parity_measured.jsonl): integer products of the data path
+bit exact; losses within 2e-5 in both operand modes (measured 4e-6); parameter gradients, layer by layer, against the
+float32 CPU oracle -- which is itself 2e-3 (median) / 7e-3 (worst layer) away from a float64 evaluation of this 63-layer
+network (tests/test_gpu_model.py) -- within 3e-2 for the exact-fp32 kernels with the cuDNN head in true fp32
+(measured 8e-3), 1e-1 with the head in PyTorch's default TF32 (4e-2), 5e-1 for fp16 tensor-core operands (2.3e-1).
 """
 import numpy as np
 import pytest
@@ -44,8 +47,13 @@ def head_tf32(request):
     torch.backends.cudnn.allow_tf32 = old
 
 
-@pytest.mark.parametrize("mode,tol", [("off", 2e-3), ("fp16", 3e-2)])
-def test_training_step_matches_oracle(cuda, mode, tol, head_tf32):
+LOSS_TOL = 2e-5
+GRAD_TOL = {("off", False): 3e-2, ("off", True): 1e-1, ("fp16", False): 5e-1, ("fp16", True): 5e-1}
+
+
+@pytest.mark.parametrize("mode", ["off", "fp16"])
+def test_training_step_matches_oracle(cuda, mode, head_tf32):
+    tol, gtol = LOSS_TOL, GRAD_TOL[(mode, head_tf32)]
     import MinkowskiEngine as ME
     from lidog_b200.me import conv as meconv
     from lidog_b200.lidog import model as M, step
@@ -107,7 +115,7 @@ def test_training_step_matches_oracle(cuda, mode, tol, head_tf32):
         assert g is not None and go is not None and torch.isfinite(g).all(), name
         if float(go.norm()) > 1e-6 * top:  # gradients that are zero up to rounding (e.g. a bias in front of a BN) carry no signal
             e = rel(g, go)
-            if e > 20 * tol:
+            if e > gtol:
                 bad.append((name, e, float(go.norm()), float(g.norm())))
     assert not bad, (top, bad[:8])
     # Adam moved the weights (|update| ~ lr on the first step) and nothing blew up

@@ -55,8 +55,15 @@ for step in "$@"; do
               timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29532 \
                 bench.py --gpus $NG --steps 8 --warmup 3 $A > ${O}_${step}_${NG}gpu.json 2> ${O}_${step}_${NG}gpu.err
               tail -1 ${O}_${step}_${NG}gpu.err | cut -c1-200; cut -c1-400 ${O}_${step}_${NG}gpu.json ;;
+    ddp_ab)   NG=${NG:-$(nvidia-smi -L | wc -l)}
+              for A in "--nccl-ctas 0" "--nccl-ctas 4" "--nccl-ctas 2" "--nccl-ctas 4 --ddp-bucket-mb 1024" "--nccl-ctas 0 --ddp-bucket-mb 1024"; do
+                echo "== $A" | tee -a ${O}_ddp_ab_${NG}gpu.txt
+                timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
+                  bench.py --gpus $NG --steps 8 --warmup 3 $A 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],1), 'scans/s', round(d['ms_per_step'],2), 'ms  e2e', round(d['e2e']['value'],1))" | tee -a ${O}_ddp_ab_${NG}gpu.txt
+              done ;;
     tests_syncbn) timeout 900 python -m pytest tests/test_gpu_syncbn.py -m gpu -q 2>&1 | tail -5 | tee ${O}_tests_syncbn.log ;;
     sanitize) bash tools/sanitize.sh ${O} ;;
+    wgdiag)   bash tools/wgrad_diag.sh 2>&1 | tee ${O}_wgrad_diag.txt | tail -30 ;;
     bisect)   bash tools/bisect_wgrad.sh 2>&1 | tee ${O}_bisect.log ;;
     *) echo "unknown step $step" ;;
   esac
