@@ -48,10 +48,13 @@ def parse():
     p.add_argument("--empty-cache", action="store_true",
                    help="call torch.cuda.empty_cache() before every step, as the reference loop does "
                         "(trainer_lighting_2d.py:147-148, clear_cache_int: 1)")
-    p.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("LIDOG_NCCL_CTAS", "4")),
-                   help="upper bound on the CTAs NCCL's all-reduce kernels may occupy (0 = NCCL's default).  The gradient "
-                        "all-reduce overlaps the backward pass; the sparse-conv kernels are persistent, one CTA per SM, so "
-                        "every SM NCCL holds is an SM they lose for the whole overlap, and 154 MB over NVLink 5 need few")
+    p.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("LIDOG_NCCL_CTAS", "0")),
+                   help="upper bound on the CTAs of NCCL's all-reduce kernels (0 = NCCL's default, the measured best: "
+                        "bounding them to 2-4 cost 7 %% at 2 GPUs, profiles/r02_c_ddp_ab_2gpu.txt)")
+    p.add_argument("--no-syncbn", action="store_true",
+                   help="diagnostic: DDP without the SyncBN conversion (NOT the reference configuration, train_lidog.py:228)")
+    p.add_argument("--same-data", action="store_true",
+                   help="diagnostic: every rank trains on rank 0's scans (no load skew between ranks at the SyncBN exchanges)")
     p.add_argument("--ddp-bucket-mb", type=int, default=int(os.environ.get("LIDOG_DDP_BUCKET_MB", "25")),
                    help="DistributedDataParallel bucket_cap_mb (25 = torch default)")
     p.add_argument("--ncu", action="store_true",
@@ -247,7 +250,8 @@ def run_ours(args):
     if lbev.CONFIG["channels_last"]:  # 4-D (2D-head) parameters only; the logical shapes do not change
         net.encoders2d.to(memory_format=torch.channels_last)
     if world > 1:  # train_lidog.py:227-231
-        net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
+        if not args.no_syncbn:
+            net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
         # gradient_as_bucket_view: the all-reduce works on the gradient storage itself (no bucket copies); same result
         ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.ddp_bucket_mb)
@@ -255,7 +259,7 @@ def run_ours(args):
         ddp = net
     trainer = step.LidogTrainer(ddp, num_classes=args.classes, shape=args.shape)
 
-    scans = synth.make_batch(args.batch, 1234 + 1000 * rank, args.shape, args.classes)
+    scans = synth.make_batch(args.batch, 1234 + (0 if args.same_data else 1000 * rank), args.shape, args.classes)
     host_pts = [torch.from_numpy(p).pin_memory() for p, _ in scans]
     host_lab = [torch.from_numpy(l).pin_memory() for _, l in scans]
     dev_pts = [p.to(dev) for p in host_pts]
@@ -397,6 +401,7 @@ def run_ours(args):
                                                            ("in-kernel over NVLink peer memory" if mepeer.active()
                                                             else "NCCL all_reduce") + ")") if world > 1 else ""),
                            "nccl_max_ctas": args.nccl_ctas if world > 1 else None,
+                           "diagnostic_flags": [f for f, on in (("no_syncbn", args.no_syncbn), ("same_data", args.same_data)) if on],
                            "ddp_bucket_cap_mb": args.ddp_bucket_mb if world > 1 else None,
                            "empty_cache_every_step": bool(args.empty_cache),
                            "arena_bytes": int(cabi.lib().lg_arena_bytes()),

@@ -56,7 +56,7 @@ for step in "$@"; do
                 bench.py --gpus $NG --steps 8 --warmup 3 $A > ${O}_${step}_${NG}gpu.json 2> ${O}_${step}_${NG}gpu.err
               tail -1 ${O}_${step}_${NG}gpu.err | cut -c1-200; cut -c1-400 ${O}_${step}_${NG}gpu.json ;;
     ddp_ab)   NG=${NG:-$(nvidia-smi -L | wc -l)}
-              for A in "--nccl-ctas 0" "--nccl-ctas 4" "--nccl-ctas 2" "--nccl-ctas 4 --ddp-bucket-mb 1024" "--nccl-ctas 0 --ddp-bucket-mb 1024"; do
+              for A in "--nccl-ctas 0" "--no-syncbn" "--same-data" "--same-data --no-syncbn"; do
                 echo "== $A" | tee -a ${O}_ddp_ab_${NG}gpu.txt
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
                   bench.py --gpus $NG --steps 8 --warmup 3 $A 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],1), 'scans/s', round(d['ms_per_step'],2), 'ms  e2e', round(d['e2e']['value'],1))" | tee -a ${O}_ddp_ab_${NG}gpu.txt
