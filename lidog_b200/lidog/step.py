@@ -10,10 +10,21 @@ uses the first point's label per voxel and the BEV image the agree-or-ignore col
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from . import losses
 from .synth import SHAPES
+
+
+_NVTX = int(os.environ.get("LIDOG_NVTX", "0"))
+
+
+def _range(name: str):
+    """NVTX range around a phase of the step (LIDOG_NVTX=1): shows up in ncu / nsys timelines."""
+    return torch.cuda.nvtx.range(name) if _NVTX and torch.cuda.is_available() else contextlib.nullcontext()
 
 
 def bev_label_image(coords4: torch.Tensor, colabels: torch.Tensor, batch_size: int, bound: float, img: int,
@@ -108,11 +119,15 @@ class LidogTrainer:
         return self.source_weights[0] * loss_3d + self.source_weights[1] * loss_bev, loss_3d, loss_bev
 
     def training_step(self, points_list, labels_list):
-        coords, feats, sem_labels, bev_labels, cm = self.voxelize(points_list, labels_list)
+        with _range("lidog/voxelize"):
+            coords, feats, sem_labels, bev_labels, cm = self.voxelize(points_list, labels_list)
         self.optimizer.zero_grad(set_to_none=True)
-        total, l3, l2 = self.forward_loss(coords, feats, sem_labels, bev_labels, len(points_list), cm)
-        total.backward()
-        self.optimizer.step()
+        with _range("lidog/forward+loss"):
+            total, l3, l2 = self.forward_loss(coords, feats, sem_labels, bev_labels, len(points_list), cm)
+        with _range("lidog/backward"):
+            total.backward()
+        with _range("lidog/adam"):
+            self.optimizer.step()
         return total.detach()
 
     def training_step_multi(self, sources):
