@@ -761,6 +761,7 @@ struct Wgrad2Args {
   const uint16_t* dY;
   float* partial;  // [chunks][K][Cin][Cout]
   int Cin, Cout, m_blocks, G, n_groups, tiles_per_chunk, umma_fmt, sa, sb, np, bmax;
+  int strided;  // offsets of a group are grp + j * n_groups (load balance) instead of a contiguous range
   int na_max;  // 32-channel sub-blocks per A stage (4; see the launcher for why not min(4, Cin / 32))
   int dbg;     // DBG instantiation only (LIDOG_WG_DBG): 1 = no dY gathers, 2 = no X gathers, 4 = no MMAs, 8 = no partial stores
   int64_t n_tiles;
@@ -776,7 +777,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
   const int grp = blockIdx.x / g.m_blocks, mb = blockIdx.x % g.m_blocks;
   const int chunk = blockIdx.y;
   const int K = g.plan.kernel_volume;
-  const int k0 = grp * g.G, k1 = min(K, k0 + g.G);
+  // The offsets of a group are STRIDED: group grp owns offsets grp, grp + n_groups, grp + 2 n_groups, ...  Contiguous
+  // ranges put the whole centre plane of a 3x3x3 kernel (offsets 9..17: 60 % of all pairs of a LiDAR map) into one or
+  // two groups: on the bench batch the heaviest CTA had 2.8x the mean number of units (190 vs 69,
+  // profiles/r02_d_wgrad_balance.txt); strided groups bring that to 1.4x for 1.5x more dY tile loads.
+  const int ng = g.strided ? g.n_groups : 1;
+  const int k0 = g.strided ? grp : grp * g.G;                                  // first offset of the group
+  const int gcount = g.strided ? (K - grp + ng - 1) / ng : min(K, k0 + g.G) - k0;  // number of offsets
   const int m0 = mb * 128;
   const int na = min(4, (g.Cin - m0) / 32);  // real 32-channel sub-blocks of the A operand
   const int nb = g.Cout / 32;
@@ -821,12 +828,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // bit j of group_mask(tile) = offset k0 + j present in the tile
+  // bit j of group_mask(tile) = offset k0 + j * ng present in the tile (K <= 64, host-checked)
   auto group_mask = [&](int64_t tile) -> uint32_t {
     const uint32_t* mw = g.plan.tile_mask + tile * g.plan.mask_words;
-    const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;
-    const uint64_t bits = (uint64_t)__ldg(mw + w0) | (w1 != w0 ? (uint64_t)__ldg(mw + w1) << 32 : 0ull);
-    return bcast0((uint32_t)(bits >> (k0 & 31)) & ((1u << (k1 - k0)) - 1u));
+    uint64_t bits = (uint64_t)__ldg(mw) | (g.plan.mask_words > 1 ? (uint64_t)__ldg(mw + 1) << 32 : 0ull);
+    bits >>= k0;
+    uint32_t m;
+    if (ng == 1) {
+      m = (uint32_t)bits;
+    } else {
+      m = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < gcount) m |= (uint32_t)((bits >> (j * ng)) & 1ull) << j;
+    }
+    return bcast0(m & ((1u << gcount) - 1u));
   };
 
   if (warp == kIdxWarp) {
@@ -835,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     uint32_t iphase = 0;
     for (int64_t tile = t0; tile < t1; tile += tstep) {
       for (uint32_t mm = group_mask(tile); mm; mm &= mm - 1) {
-        const int k = k0 + __ffs(mm) - 1;
+        const int k = k0 + (__ffs(mm) - 1) * ng;
         mbar_wait(&emptyI[slot], iphase ^ 1, g.err, 16);
         if (elect_one()) {
           mbar_arrive_expect_tx(&fullI[slot], kIdxSlotBytes);
@@ -1007,8 +1023,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad2(const Wgrad2Args g) {
     const int ci = m0 + warp * 32 + lane;
     mbar_wait(done, 0, g.err, 15);
     tc_fence_after();
-    for (int k = k0; k < k1; ++k) {
-      const int j = k - k0;
+    for (int j = 0; j < gcount; ++j) {
+      const int k = k0 + j * ng;
       const bool have = (started >> j) & 1u;
       float* prow = g.partial + (((int64_t)chunk * K + k) * g.Cin + (ci < g.Cin ? ci : 0)) * g.Cout;
       const uint32_t taddr = tmem_base + j * g.Cout + ((uint32_t)(warp * 32) << 16);
@@ -1066,8 +1082,9 @@ int debug_profile(long long* out16, int reset) {
 //   LIDOG_G2_RING    0 = the ring shape of the first validated lean kernel (32 id slots, 3 weight stages when they fit)
 //   LIDOG_G2_T       pin the tiles per super-tile (parity tests sweep the multi-tile schedules on small inputs)
 //   LIDOG_WG_CTAS / LIDOG_WG_BATCH / LIDOG_WG_SB   wgrad CTA target / MMA-warp batch / dY ring depth
+//   LIDOG_WG_STRIDED 0 = contiguous offset groups (round 1)
 struct Switches {
-  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb, wg_na4, wg_sa, wg_dbg;
+  int dbg, acc_sets, opt, force_sb, force_pc, ring_new, force_t, wg_ctas, wg_batch, mma2, wg_sb, wg_na4, wg_sa, wg_dbg, wg_strided;
 };
 static const Switches& switches() {
   static const Switches sw = {env_int("LIDOG_DBG", 0),     env_int("LIDOG_ACC_SETS", 2), env_int("LIDOG_G2_OPT", 3),
@@ -1075,7 +1092,7 @@ static const Switches& switches() {
                               env_int("LIDOG_G2_T", 0),    env_int("LIDOG_WG_CTAS", 0),  env_int("LIDOG_WG_BATCH", 4),
                               env_int("LIDOG_G2_MMA2", 0), env_int("LIDOG_WG_SB", 0),
                               env_int("LIDOG_WG_NA4", 1),  env_int("LIDOG_WG_SA", 0),
-                              env_int("LIDOG_WG_DBG", 0)};
+                              env_int("LIDOG_WG_DBG", 0),  env_int("LIDOG_WG_STRIDED", 1)};
   return sw;
 }
 
@@ -1306,6 +1323,11 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   // the neighbouring stages, and the full-scale parity test (tests/test_gpu_fullscale.py) measured 0.3-2.5 % error in
   // dW -- bisected on hardware (profiles/r02_b_wgrad_bisect.log); the switch stays for that record only.
   g.na_max = switches().wg_na4 ? 4 : (Cin / 32 < 4 ? Cin / 32 : 4);
+  g.strided = switches().wg_strided ? 1 : 0;
+  if (plan->kernel_volume > 64) {
+    set_error("lg_conv_wgrad_tc: kernel volume %d > 64 is not on the tensor-core path", plan->kernel_volume);
+    return LG_ERR_UNSUPPORTED;
+  }
   const size_t stageA = (size_t)g.na_max * kSub, stageB = (size_t)(Cout / 32) * kSub;
   // dY ring: 3 stages when 4 X stages still fit next to them (the MMA warp waited on this ring, see the dY producer)
   g.sb = (4 * stageA + 3 * stageB + wgrad_tail_bytes(4, 3) <= kSmemBudget) ? 3 : 2;
