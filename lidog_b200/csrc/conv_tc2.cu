@@ -1323,7 +1323,10 @@ int launch_wgrad_tc2(const lgConvPlan* plan, const void* X16, int Cin, const voi
   // the neighbouring stages, and the full-scale parity test (tests/test_gpu_fullscale.py) measured 0.3-2.5 % error in
   // dW -- bisected on hardware (profiles/r02_b_wgrad_bisect.log); the switch stays for that record only.
   g.na_max = switches().wg_na4 ? 4 : (Cin / 32 < 4 ? Cin / 32 : 4);
-  g.strided = switches().wg_strided ? 1 : 0;
+  // strided groups where there are enough groups for the imbalance to matter: measured -7 ... -20 % on the 96- / 128- /
+  // 256-channel layers (5 ... 14 groups), +15 % on the 32-channel ones (4 groups of 7 offsets, already balanced, and
+  // every extra dY tile load is pure HBM cost there) -- profiles/r02_d_layer_table_strided.txt
+  g.strided = (switches().wg_strided && g.n_groups >= 5) ? 1 : 0;
   if (plan->kernel_volume > 64) {
     set_error("lg_conv_wgrad_tc: kernel volume %d > 64 is not on the tensor-core path", plan->kernel_volume);
     return LG_ERR_UNSUPPORTED;
