@@ -57,6 +57,10 @@ def parse():
                    help="diagnostic: every rank trains on rank 0's scans (no load skew between ranks at the SyncBN exchanges)")
     p.add_argument("--ddp-bucket-mb", type=int, default=int(os.environ.get("LIDOG_DDP_BUCKET_MB", "25")),
                    help="DistributedDataParallel bucket_cap_mb (25 = torch default)")
+    p.add_argument("--ddp-broadcast-buffers", type=int, default=1,
+                   help="DDP broadcast_buffers (1 = torch / Lightning default: rank 0's BN running statistics are "
+                        "re-broadcast before every forward; 0 = skip it -- training-mode results are identical)")
+    p.add_argument("--ddp-static-graph", type=int, default=0, help="DDP static_graph")
     p.add_argument("--ncu", action="store_true",
                    help="profiling run: 1 warm-up + 1 step between cudaProfilerStart/Stop, no e2e / CPU legs "
                         "(use with ncu --profile-from-start off; numbers printed under ncu are not bench values)")
@@ -259,7 +263,9 @@ def run_ours(args):
             net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
         # gradient_as_bucket_view: the all-reduce works on the gradient storage itself (no bucket copies); same result
         ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=args.ddp_bucket_mb)
+                                                        bucket_cap_mb=args.ddp_bucket_mb,
+                                                        broadcast_buffers=bool(args.ddp_broadcast_buffers),
+                                                        static_graph=bool(args.ddp_static_graph))
     else:
         ddp = net
     trainer = step.LidogTrainer(ddp, num_classes=args.classes, shape=args.shape)

@@ -174,6 +174,16 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, double count, con
   }
 }
 
+// The pre-activation value of a layer WITHOUT a residual, exactly as k_bn_apply computes it (same fmaf, same operand
+// order): the backward recomputes the ReLU mask from x (and x2) instead of reading y -- 8 of 30 bytes per element.
+__device__ __forceinline__ float4 preact(float4 v, float4 sc, float4 sh) {
+  return make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+}
+__device__ __forceinline__ float4 preact_add(float4 o, float4 v2, float4 s2, float4 h2) {
+  o.x += fmaf(v2.x, s2.x, h2.x), o.y += fmaf(v2.y, s2.y, h2.y), o.z += fmaf(v2.z, s2.z, h2.z), o.w += fmaf(v2.w, s2.w, h2.w);
+  return o;
+}
+
 // y = act(x * scale + shift [+ x2 * scale2 + shift2] [+ res]); st = [mean, invstd, scale, shift] x C.
 // A thread handles kApplyU float4 a block-width apart: all loads are issued before the first use, so a CTA
 // keeps 4x the bytes in flight of the one-element-per-thread form (HBM-latency bound otherwise).
@@ -200,12 +210,10 @@ __global__ void __launch_bounds__(256)
     if (i >= n4) break;
     const int c = (int)(i % Cq) * 4;
     const float4 sc = *reinterpret_cast<const float4*>(st + 2 * C + c), sh = *reinterpret_cast<const float4*>(st + 3 * C + c);
-    float4 o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z),
-                           fmaf(v[u].w, sc.w, sh.w));
+    float4 o = preact(v[u], sc, sh);
     if (x2) {
       const float4 s2 = *reinterpret_cast<const float4*>(st2 + 2 * C + c), h2 = *reinterpret_cast<const float4*>(st2 + 3 * C + c);
-      o.x += fmaf(v2[u].x, s2.x, h2.x), o.y += fmaf(v2[u].y, s2.y, h2.y), o.z += fmaf(v2[u].z, s2.z, h2.z),
-          o.w += fmaf(v2[u].w, s2.w, h2.w);
+      o = preact_add(o, v2[u], s2, h2);
     }
     if (res) o.x += r[u].x, o.y += r[u].y, o.z += r[u].z, o.w += r[u].w;
     if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
@@ -220,7 +228,7 @@ __device__ __forceinline__ float4 masked(float4 dy, float4 y, int relu) {
 }
 
 // partial row of a block: [sum g | sum g*(x-mean) | sum g*(x2-mean2) | max|g| | max|x-mean| | max|x2-mean2|] x C
-template <bool DENSE>
+template <bool DENSE, bool RECOMP>  // RECOMP: ReLU mask from x (y is not read; layers without a residual)
 __global__ void __launch_bounds__(kBnThreads)
     k_bn_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                    const float* __restrict__ st, const float* __restrict__ x2, const float* __restrict__ st2, int relu,
@@ -234,12 +242,24 @@ __global__ void __launch_bounds__(kBnThreads)
   if (g.active) {
     const float4 mu = *reinterpret_cast<const float4*>(st + g.cq * 4);
     const float4 mu2 = x2 ? *reinterpret_cast<const float4*>(st2 + g.cq * 4) : z;
+    float4 sc = z, sh = z, sc2 = z, sh2 = z;
+    if (RECOMP) {
+      sc = *reinterpret_cast<const float4*>(st + 2 * C + g.cq * 4), sh = *reinterpret_cast<const float4*>(st + 3 * C + g.cq * 4);
+      if (x2)
+        sc2 = *reinterpret_cast<const float4*>(st2 + 2 * C + g.cq * 4), sh2 = *reinterpret_cast<const float4*>(st2 + 3 * C + g.cq * 4);
+    }
 #pragma unroll 4
     for (int64_t r = g.r0 + g.ry; r < g.r1; r += g.rpp) {
       const int64_t i = r * (C >> 2) + g.cq;
-      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + (DENSE ? i : r * dy_ld4 + g.cq)),
-                               relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z, relu);
       const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float4 yv = z;
+      if (RECOMP) {
+        yv = preact(v, sc, sh);
+        if (x2) yv = preact_add(yv, __ldg(reinterpret_cast<const float4*>(x2) + i), sc2, sh2);
+      } else if (relu) {
+        yv = __ldg(reinterpret_cast<const float4*>(y) + i);
+      }
+      const float4 gy = masked(__ldg(reinterpret_cast<const float4*>(dy) + (DENSE ? i : r * dy_ld4 + g.cq)), yv, relu);
       const float4 d = make_float4(v.x - mu.x, v.y - mu.y, v.z - mu.z, v.w - mu.w);
       sg.x += gy.x, sg.y += gy.y, sg.z += gy.z, sg.w += gy.w;
       sgx.x += gy.x * d.x, sgx.y += gy.y * d.y, sgx.z += gy.z * d.z, sgx.w += gy.w * d.w;
@@ -344,11 +364,12 @@ __global__ void __launch_bounds__(256)
     const int64_t i = base + u * 256;
     if (i < n4) {
       gd[u] = __ldg(reinterpret_cast<const float4*>(dy) + (dy_ld4 == Cq ? i : (i / Cq) * dy_ld4 + i % Cq));
-      gy[u] = relu ? __ldg(reinterpret_cast<const float4*>(y) + i) : z;
+      gy[u] = (relu && y) ? __ldg(reinterpret_cast<const float4*>(y) + i) : z;
       vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
       if (x2) vx2[u] = __ldg(reinterpret_cast<const float4*>(x2) + i);
     }
   }
+  const bool recomp = relu && !y;  // no residual in the forward: the mask is the sign of the recomputed pre-activation
   const float s1 = (dx16 && scale) ? scale[0] : 1.f, s2 = (dx2_16 && scale2) ? scale2[0] : 1.f,
               sr = (dres16 && scale_r) ? scale_r[0] : 1.f;
 #pragma unroll
@@ -356,6 +377,12 @@ __global__ void __launch_bounds__(256)
     const int64_t i = base + u * 256;
     if (i >= n4) break;
     const int c = (int)(i % Cq) * 4;
+    if (recomp) {
+      gy[u] = preact(vx[u], *reinterpret_cast<const float4*>(st + 2 * C + c), *reinterpret_cast<const float4*>(st + 3 * C + c));
+      if (x2)
+        gy[u] = preact_add(gy[u], vx2[u], *reinterpret_cast<const float4*>(st2 + 2 * C + c),
+                           *reinterpret_cast<const float4*>(st2 + 3 * C + c));
+    }
     const float4 g = masked(gd[u], gy[u], relu);
     {
       const float4 v = vx[u];
@@ -671,7 +698,7 @@ extern "C" int lg_bn_bwd_stats(const float* dy, const float* y, const float* x, 
   LG_CHECK_ARG(workspace && workspace_bytes >= lg_bn_workspace(n, C), "lg_bn_bwd_stats: workspace too small");
   const int nb = bn_blocks(n);
   float* partial = (float*)workspace;
-  k_bn_bwd_stats<true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
+  k_bn_bwd_stats<true, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
   LG_LAUNCH_OK();
   k_bn_bwd_reduce<<<ceil_div(6 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>(partial, nb, C, sums, maxes);
   LG_LAUNCH_OK();
@@ -828,8 +855,9 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   int rc = bn_check(n > 0 ? n : 1, C, "lg_bn_layer_backward");
   if (rc) return rc;
   LG_CHECK_ARG(n >= 0 && a && a->stats && scales && (!b || b->stats) &&
-                   (n == 0 || (dy && a->x && a->dx && (!relu || y) && (!b || (b->x && b->dx)))),
+                   (n == 0 || (dy && a->x && a->dx && (!b || (b->x && b->dx)))),
                "lg_bn_layer_backward: null pointer");
+  LG_CHECK_ARG(!(relu && dres && !y), "lg_bn_layer_backward: a layer with a residual needs y for its ReLU mask");
   LG_CHECK_ARG(dy_ld >= C && dy_ld % 4 == 0 && ((uintptr_t)dy & 15) == 0,
                "lg_bn_layer_backward: dy needs a row pitch >= C that is a multiple of 4 floats and 16-byte alignment");
   int sm = 0;
@@ -845,12 +873,21 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   if (rc) return rc;
   const int nb = bn_blocks(n);
   float* partial = (float*)arena_take(&ar, sizeof(float) * (size_t)kBnMaxBlocks * 6 * C);
-  if (dy_ld == C)
-    k_bn_bwd_stats<true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
-                                                                  b ? b->stats : nullptr, relu, n, C, partial, C >> 2);
-  else
-    k_bn_bwd_stats<false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, b ? b->x : nullptr,
-                                                                   b ? b->stats : nullptr, relu, n, C, partial, dy_ld >> 2);
+  const bool recomp = relu && !y;  // see lidog_b200.h: y == NULL says "the forward had no residual"
+  const float* x2p = b ? b->x : nullptr;
+  const float* st2p = b ? b->stats : nullptr;
+  const int64_t ld4 = dy_ld >> 2;
+  if (dy_ld == C) {
+    if (recomp)
+      k_bn_bwd_stats<true, true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
+    else
+      k_bn_bwd_stats<true, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
+  } else {
+    if (recomp)
+      k_bn_bwd_stats<false, true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
+    else
+      k_bn_bwd_stats<false, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
+  }
   LG_LAUNCH_OK();
   BnBwdTail t;
   memset(&t, 0, sizeof(t));

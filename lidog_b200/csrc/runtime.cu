@@ -46,6 +46,10 @@ int device_rt(DeviceRt** out) {
   DeviceRt& r = g_rt[dev];
   if (!r.ready) {
     LG_CUDA_OK(cudaDeviceGetAttribute(&r.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    // Experiment switch: persistent grids leave this many SMs free (for NCCL's CTAs under DDP; a persistent CTA queued
+    // behind a long all-reduce CTA delays the completion of its whole grid).
+    int reserve = env_int("LIDOG_SM_RESERVE", 0);
+    if (reserve > 0 && reserve < r.sm_count) r.sm_count -= reserve;
     LG_CUDA_OK(cudaMalloc(&r.err_word, sizeof(int)));
     LG_CUDA_OK(cudaMemset(r.err_word, 0, sizeof(int)));
     LG_CUDA_OK(cudaMalloc(&r.counters, kCounterSlots * 8 * sizeof(int)));

@@ -34,7 +34,9 @@ import ctypes as _C
 
 CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1")),
           # 1 = one library call per layer each way (lg_bn_layer_forward / _backward); 0 = fine-grained calls
-          "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1"))}
+          "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1")),
+          # 1 = layers without a residual recompute the ReLU mask from x in the backward instead of reading y
+          "recompute_mask": int(os.environ.get("LIDOG_BN_RECOMPUTE_MASK", "1"))}
 C_byref = _C.byref
 
 from ._grad16 import publish_grad16
@@ -142,7 +144,10 @@ class FusedBNFunction(torch.autograd.Function):
             cabi.count_launches("lg_bn_layer_forward", 1 + (1 if sp_a is not None else 2) +
                                 (0 if x2 is None else (1 if sp_b is not None else 2)))
         box["y16"], box["fmt"] = y16, fmt
-        ctx.save_for_backward(x, x2, y if relu else None, st_a, st_b, w, w2)
+        # y is saved only where the backward needs it for the ReLU mask: without a residual the library recomputes
+        # the mask from x (lg_bn_layer_backward with y = NULL)
+        keep_y = relu and (res is not None or not CONFIG["recompute_mask"])
+        ctx.save_for_backward(x, x2, y if keep_y else None, st_a, st_b, w, w2)
         ctx.meta = (relu, res is not None, fmt, ex)
         return y
 

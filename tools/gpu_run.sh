@@ -55,10 +55,13 @@ for step in "$@"; do
               timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29532 \
                 bench.py --gpus $NG --steps 8 --warmup 3 $A > ${O}_${step}_${NG}gpu.json 2> ${O}_${step}_${NG}gpu.err
               tail -1 ${O}_${step}_${NG}gpu.err | cut -c1-200; cut -c1-400 ${O}_${step}_${NG}gpu.json ;;
-    ddp_ab)   NG=${NG:-$(nvidia-smi -L | wc -l)}
-              for A in "--nccl-ctas 0" "--no-syncbn" "--same-data" "--same-data --no-syncbn"; do
-                echo "== $A" | tee -a ${O}_ddp_ab_${NG}gpu.txt
-                timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
+    ddp_ab)   NG=${NG:-$(nvidia-smi -L | wc -l)}   # variants: "ENV=.. ENV=..|bench flags"
+              for V in "|" "|--ddp-broadcast-buffers 0" "|--ddp-broadcast-buffers 0 --ddp-static-graph 1" \
+                       "LIDOG_SM_RESERVE=8|--ddp-broadcast-buffers 0" "LIDOG_SM_RESERVE=16|--ddp-broadcast-buffers 0" \
+                       "|--ddp-broadcast-buffers 0 --no-syncbn" "|"; do
+                E="${V%%|*}"; A="${V#*|}"
+                echo "== env[$E] $A" | tee -a ${O}_ddp_ab_${NG}gpu.txt
+                timeout 600 env $E python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
                   bench.py --gpus $NG --steps 8 --warmup 3 $A 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],1), 'scans/s', round(d['ms_per_step'],2), 'ms  e2e', round(d['e2e']['value'],1))" | tee -a ${O}_ddp_ab_${NG}gpu.txt
               done ;;
     tests_syncbn) timeout 900 python -m pytest tests/test_gpu_syncbn.py -m gpu -q 2>&1 | tail -5 | tee ${O}_tests_syncbn.log ;;
