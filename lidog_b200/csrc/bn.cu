@@ -228,8 +228,9 @@ __device__ __forceinline__ float4 masked(float4 dy, float4 y, int relu) {
 }
 
 // partial row of a block: [sum g | sum g*(x-mean) | sum g*(x2-mean2) | max|g| | max|x-mean| | max|x2-mean2|] x C
-template <bool DENSE, bool RECOMP>  // RECOMP: ReLU mask from x (y is not read; layers without a residual)
-__global__ void __launch_bounds__(kBnThreads)
+// RECOMP: ReLU mask from x (y is not read; layers without a residual).  HAS2: second BN branch (x2) present.
+template <bool DENSE, bool RECOMP, bool HAS2>
+__global__ void __launch_bounds__(kBnThreads, 4)  // the grid is 4 blocks per SM (kBnMaxBlocks): all of them must be resident
     k_bn_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                    const float* __restrict__ st, const float* __restrict__ x2, const float* __restrict__ st2, int relu,
                    int64_t n, int C, float* __restrict__ partial, int64_t dy_ld4) {
@@ -241,11 +242,11 @@ __global__ void __launch_bounds__(kBnThreads)
   float4 sg = z, sgx = z, sgx2 = z, mg = z, mx = z, mx2 = z;
   if (g.active) {
     const float4 mu = *reinterpret_cast<const float4*>(st + g.cq * 4);
-    const float4 mu2 = x2 ? *reinterpret_cast<const float4*>(st2 + g.cq * 4) : z;
+    const float4 mu2 = HAS2 ? *reinterpret_cast<const float4*>(st2 + g.cq * 4) : z;
     float4 sc = z, sh = z, sc2 = z, sh2 = z;
     if (RECOMP) {
       sc = *reinterpret_cast<const float4*>(st + 2 * C + g.cq * 4), sh = *reinterpret_cast<const float4*>(st + 3 * C + g.cq * 4);
-      if (x2)
+      if (HAS2)
         sc2 = *reinterpret_cast<const float4*>(st2 + 2 * C + g.cq * 4), sh2 = *reinterpret_cast<const float4*>(st2 + 3 * C + g.cq * 4);
     }
 #pragma unroll 4
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kBnThreads)
       float4 yv = z;
       if (RECOMP) {
         yv = preact(v, sc, sh);
-        if (x2) yv = preact_add(yv, __ldg(reinterpret_cast<const float4*>(x2) + i), sc2, sh2);
+        if (HAS2) yv = preact_add(yv, __ldg(reinterpret_cast<const float4*>(x2) + i), sc2, sh2);
       } else if (relu) {
         yv = __ldg(reinterpret_cast<const float4*>(y) + i);
       }
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kBnThreads)
       sgx.x += gy.x * d.x, sgx.y += gy.y * d.y, sgx.z += gy.z * d.z, sgx.w += gy.w * d.w;
       mg = make_float4(fmaxf(mg.x, fabsf(gy.x)), fmaxf(mg.y, fabsf(gy.y)), fmaxf(mg.z, fabsf(gy.z)), fmaxf(mg.w, fabsf(gy.w)));
       mx = make_float4(fmaxf(mx.x, fabsf(d.x)), fmaxf(mx.y, fabsf(d.y)), fmaxf(mx.z, fabsf(d.z)), fmaxf(mx.w, fabsf(d.w)));
-      if (x2) {
+      if (HAS2) {
         const float4 v2 = __ldg(reinterpret_cast<const float4*>(x2) + i);
         const float4 d2 = make_float4(v2.x - mu2.x, v2.y - mu2.y, v2.z - mu2.z, v2.w - mu2.w);
         sgx2.x += gy.x * d2.x, sgx2.y += gy.y * d2.y, sgx2.z += gy.z * d2.z, sgx2.w += gy.w * d2.w;
@@ -698,7 +699,10 @@ extern "C" int lg_bn_bwd_stats(const float* dy, const float* y, const float* x, 
   LG_CHECK_ARG(workspace && workspace_bytes >= lg_bn_workspace(n, C), "lg_bn_bwd_stats: workspace too small");
   const int nb = bn_blocks(n);
   float* partial = (float*)workspace;
-  k_bn_bwd_stats<true, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
+  if (x2)
+    k_bn_bwd_stats<true, false, true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
+  else
+    k_bn_bwd_stats<true, false, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, x, stats, x2, stats2, relu, n, C, partial, C >> 2);
   LG_LAUNCH_OK();
   k_bn_bwd_reduce<<<ceil_div(6 * C, kRedX), dim3(kRedX, kRedY), 0, stream>>>(partial, nb, C, sums, maxes);
   LG_LAUNCH_OK();
@@ -877,17 +881,20 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   const float* x2p = b ? b->x : nullptr;
   const float* st2p = b ? b->stats : nullptr;
   const int64_t ld4 = dy_ld >> 2;
-  if (dy_ld == C) {
-    if (recomp)
-      k_bn_bwd_stats<true, true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
-    else
-      k_bn_bwd_stats<true, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
-  } else {
-    if (recomp)
-      k_bn_bwd_stats<false, true><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
-    else
-      k_bn_bwd_stats<false, false><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4);
+#define LG_BWD_STATS(D, R, H) \
+  k_bn_bwd_stats<D, R, H><<<nb, kBnThreads, red_smem(C), stream>>>(dy, y, a->x, a->stats, x2p, st2p, relu, n, C, partial, ld4)
+  const int variant = (dy_ld == C ? 4 : 0) | (recomp ? 2 : 0) | (b ? 1 : 0);
+  switch (variant) {
+    case 0: LG_BWD_STATS(false, false, false); break;
+    case 1: LG_BWD_STATS(false, false, true); break;
+    case 2: LG_BWD_STATS(false, true, false); break;
+    case 3: LG_BWD_STATS(false, true, true); break;
+    case 4: LG_BWD_STATS(true, false, false); break;
+    case 5: LG_BWD_STATS(true, false, true); break;
+    case 6: LG_BWD_STATS(true, true, false); break;
+    default: LG_BWD_STATS(true, true, true); break;
   }
+#undef LG_BWD_STATS
   LG_LAUNCH_OK();
   BnBwdTail t;
   memset(&t, 0, sizeof(t));

@@ -145,8 +145,9 @@ class FusedBNFunction(torch.autograd.Function):
                                 (0 if x2 is None else (1 if sp_b is not None else 2)))
         box["y16"], box["fmt"] = y16, fmt
         # y is saved only where the backward needs it for the ReLU mask: without a residual the library recomputes
-        # the mask from x (lg_bn_layer_backward with y = NULL)
-        keep_y = relu and (res is not None or not CONFIG["recompute_mask"])
+        # the mask from x (lg_bn_layer_backward with y = NULL; the two-branch form of that kernel spills registers,
+        # so the three downsample layers keep reading y)
+        keep_y = relu and (res is not None or x2 is not None or not CONFIG["recompute_mask"])
         ctx.save_for_backward(x, x2, y if keep_y else None, st_a, st_b, w, w2)
         ctx.meta = (relu, res is not None, fmt, ex)
         return y

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One parameterised GPU session script (replaces the per-session one-offs of round 1):
 #   gpurun --timeout 1500 -- 'bash tools/gpu_run.sh <tag> <step> [<step> ...]'
-# steps: tests | smoke | bench | bench_ab | host | micro | layers | launches | ncu_gemm | ncu_wgrad | ncu_hbm | sanitize |
+# steps: tests | smoke | bench | bench_ab | host | micro | layers | launches | ncu_gemm | ncu_wgrad | ncu_hbm | ncu_hbm2 (light metrics, every HBM kernel of a step) | sanitize |
 #        bench_cfg0 | bench_nuscenes | bench_mix3d | empty_cache
 # Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 tag=$1; shift
@@ -42,6 +42,12 @@ for step in "$@"; do
     ncu_hbm)  timeout 900 ncu --set full --clock-control none --profile-from-start off \
                 -k regex:'k_bn_|k_neighbors|k_insert|k_conv_c1|k_scan' -c 70 -o ${O}_ncu_hbm -f python bench.py --ncu > ${O}_ncu4.log 2>&1
               python tools/ncu_summary.py ${O}_ncu_hbm.ncu-rep > ${O}_ncu_hbm_kernels.txt; ls -la ${O}_ncu_hbm*; rm -f ${O}_ncu_hbm.ncu-rep ;;
+    ncu_hbm2) timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum \
+                --clock-control none --profile-from-start off \
+                -k regex:'k_bn_|k_neighbors|k_insert|k_conv_c1|k_scan|k_bev_|k_dice|k_reduce_partials|k_head_|k_quantize|k_permute|k_sort_keys|k_relabel|k_inverse|k_up2' \
+                -c 600 -o ${O}_ncu_hbm2 -f python bench.py --ncu > ${O}_ncu6.log 2>&1
+              python tools/ncu_summary.py ${O}_ncu_hbm2.ncu-rep > ${O}_ncu_hbm2_kernels.txt; python tools/hbm_summary.py ${O}_ncu_hbm2_kernels.txt > ${O}_hbm_summary.txt
+              ls -la ${O}_ncu_hbm2*; rm -f ${O}_ncu_hbm2.ncu-rep; head -40 ${O}_hbm_summary.txt ;;
     ncu_bev)  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
                 -k regex:'k_bev_' -c 4 -o ${O}_ncu_bev -f python bench.py --ncu > ${O}_ncu5.log 2>&1
               python tools/ncu_summary.py ${O}_ncu_bev.ncu-rep > ${O}_ncu_bev.txt; ncu -i ${O}_ncu_bev.ncu-rep --page source --csv > ${O}_ncu_bev_source.csv 2>/dev/null
