@@ -161,6 +161,48 @@ __global__ void __launch_bounds__(256)
   dW[i] = out_scale ? s * out_scale[0] : s;
 }
 
+// float4 form: block = 64 element-quads x 4 parts; part p folds the chunks of its contiguous quarter (8 independent
+// 16-byte loads in flight per thread), then the four part sums are added in part order through shared memory:
+// fixed order, 2.5 GB of partials per step read at HBM speed instead of one 4-byte load per thread and chunk.
+constexpr int kRpX = 64, kRpParts = 4;
+__global__ void __launch_bounds__(kRpX* kRpParts)
+    k_reduce_partials4(const float4* __restrict__ partial, int n_chunks, int64_t n4, const float* __restrict__ out_scale,
+                       float4* __restrict__ dW) {
+  __shared__ float4 sm[kRpParts][kRpX];
+  const int64_t i = (int64_t)blockIdx.x * kRpX + threadIdx.x;
+  const int per = (n_chunks + kRpParts - 1) / kRpParts;
+  const int c0 = threadIdx.y * per, c1 = min(n_chunks, c0 + per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(partial + (int64_t)(c + u) * n4 + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s.x += v[u].x, s.y += v[u].y, s.z += v[u].z, s.w += v[u].w;
+    }
+    for (; c < c1; ++c) {
+      const float4 v = __ldcs(partial + (int64_t)c * n4 + i);
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n4) {
+#pragma unroll
+    for (int p = 1; p < kRpParts; ++p) {
+      const float4 v = sm[p][threadIdx.x];
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    if (out_scale) {
+      const float k = out_scale[0];
+      s.x *= k, s.y *= k, s.z *= k, s.w *= k;
+    }
+    dW[i] = s;
+  }
+}
+
 
 // ------------------------------------------------------------------------------------ Cin == 1 stem
 // conv0p1s1 of MinkUNet34 (utils/models/minkunet_bev.py:57: kernel 5, 1 -> 32 channels, 125 offsets) is a
@@ -490,8 +532,14 @@ int wgrad_chunks(const lgConvPlan* plan, int* tiles_per_chunk) {
 
 int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
                            cudaStream_t stream) {
-  k_reduce_partials<<<(unsigned)ceil_div(n_elems, 256), 256, 0, stream>>>(partial, n_chunks, n_elems, 0.f, out_scale,
-                                                                          dW);
+  if (n_elems % 4 == 0 && (((uintptr_t)partial | (uintptr_t)dW) & 15) == 0 && n_chunks >= 8) {
+    const int64_t n4 = n_elems / 4;
+    k_reduce_partials4<<<(unsigned)ceil_div(n4, kRpX), dim3(kRpX, kRpParts), 0, stream>>>(
+        reinterpret_cast<const float4*>(partial), n_chunks, n4, out_scale, reinterpret_cast<float4*>(dW));
+  } else {
+    k_reduce_partials<<<(unsigned)ceil_div(n_elems, 256), 256, 0, stream>>>(partial, n_chunks, n_elems, 0.f, out_scale,
+                                                                            dW);
+  }
   LG_LAUNCH_OK();
   return LG_OK;
 }

@@ -31,6 +31,14 @@ for step in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
                 --log-file ${O}_launches.csv python bench.py --ncu > ${O}_ncu1.log 2>&1
               python tools/launch_summary.py ${O}_launches.csv > ${O}_launch_summary.txt 2>&1; head -45 ${O}_launch_summary.txt ;;
+    envsweep) # ENVS="A=1 B=2;A=3" : one launch list per ';'-separated environment, restricted to the kernels in $KSEL
+              IFS=';' read -ra VARS <<< "${ENVS:-;}"
+              for E in "${VARS[@]}"; do
+                echo "== env[$E]" | tee -a ${O}_envsweep.txt
+                timeout 600 env $E ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+                  -k regex:"${KSEL:-k_wgrad2|k_reduce_partials}" --log-file ${O}_sweep.csv python bench.py --ncu > ${O}_ncu7.log 2>&1
+                python tools/launch_summary.py ${O}_sweep.csv 2>&1 | head -6 | tee -a ${O}_envsweep.txt
+              done; rm -f ${O}_sweep.csv ;;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm2 -s 58 -c 2 \
                 -o ${O}_ncu_gemm2 -f python bench.py --ncu > ${O}_ncu2.log 2>&1
               python tools/ncu_summary.py ${O}_ncu_gemm2.ncu-rep > ${O}_ncu_gemm2.txt; ncu -i ${O}_ncu_gemm2.ncu-rep --page source --csv > ${O}_ncu_gemm2_source.csv 2>/dev/null
