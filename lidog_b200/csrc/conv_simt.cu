@@ -532,7 +532,7 @@ int wgrad_chunks(const lgConvPlan* plan, int* tiles_per_chunk) {
 
 int launch_reduce_partials(const float* partial, int n_chunks, int64_t n_elems, const float* out_scale, float* dW,
                            cudaStream_t stream) {
-  if (n_elems % 4 == 0 && (((uintptr_t)partial | (uintptr_t)dW) & 15) == 0 && n_chunks >= 8) {
+  if (n_elems % 4 == 0 && (((uintptr_t)partial | (uintptr_t)dW) & 15) == 0) {
     const int64_t n4 = n_elems / 4;
     k_reduce_partials4<<<(unsigned)ceil_div(n4, kRpX), dim3(kRpX, kRpParts), 0, stream>>>(
         reinterpret_cast<const float4*>(partial), n_chunks, n4, out_scale, reinterpret_cast<float4*>(dW));
