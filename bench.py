@@ -57,9 +57,11 @@ def parse():
                    help="diagnostic: every rank trains on rank 0's scans (no load skew between ranks at the SyncBN exchanges)")
     p.add_argument("--ddp-bucket-mb", type=int, default=int(os.environ.get("LIDOG_DDP_BUCKET_MB", "25")),
                    help="DistributedDataParallel bucket_cap_mb (25 = torch default)")
-    p.add_argument("--ddp-broadcast-buffers", type=int, default=1,
-                   help="DDP broadcast_buffers (1 = torch / Lightning default: rank 0's BN running statistics are "
-                        "re-broadcast before every forward; 0 = skip it -- training-mode results are identical)")
+    p.add_argument("--ddp-buffers", choices=["flat", "ddp", "off"], default="flat",
+                   help="how rank 0's module buffers (BN running statistics) reach the other ranks before every "
+                        "forward: 'ddp' = DistributedDataParallel(broadcast_buffers=True), ~190 tensors one by one; "
+                        "'flat' = same semantics, buffers are views of one flat tensor per dtype (2 broadcasts); "
+                        "'off' = no broadcast")
     p.add_argument("--ddp-static-graph", type=int, default=0, help="DDP static_graph")
     p.add_argument("--ncu", action="store_true",
                    help="profiling run: 1 warm-up + 1 step between cudaProfilerStart/Stop, no e2e / CPU legs "
@@ -262,13 +264,12 @@ def run_ours(args):
         if not args.no_syncbn:
             net = ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net)
         # gradient_as_bucket_view: the all-reduce works on the gradient storage itself (no bucket copies); same result
-        ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=args.ddp_bucket_mb,
-                                                        broadcast_buffers=bool(args.ddp_broadcast_buffers),
-                                                        static_graph=bool(args.ddp_static_graph))
+        from lidog_b200.lidog import ddp as lddp
+        ddp, flat_buffers = lddp.wrap(net, device_ids=[local], buffers=args.ddp_buffers, gradient_as_bucket_view=True,
+                                      bucket_cap_mb=args.ddp_bucket_mb, static_graph=bool(args.ddp_static_graph))
     else:
-        ddp = net
-    trainer = step.LidogTrainer(ddp, num_classes=args.classes, shape=args.shape)
+        ddp, flat_buffers = net, None
+    trainer = step.LidogTrainer(ddp, num_classes=args.classes, shape=args.shape, buffer_sync=flat_buffers)
 
     scans = synth.make_batch(args.batch, 1234 + (0 if args.same_data else 1000 * rank), args.shape, args.classes)
     host_pts = [torch.from_numpy(p).pin_memory() for p, _ in scans]
@@ -414,6 +415,10 @@ def run_ours(args):
                            "nccl_max_ctas": args.nccl_ctas if world > 1 else None,
                            "diagnostic_flags": [f for f, on in (("no_syncbn", args.no_syncbn), ("same_data", args.same_data)) if on],
                            "ddp_bucket_cap_mb": args.ddp_bucket_mb if world > 1 else None,
+                           "ddp_buffers": ({"flat": "rank 0's buffers broadcast before every forward as 2 flat tensors "
+                                                    "(lidog/ddp.py; same semantics as DDP broadcast_buffers=True)",
+                                            "ddp": "DistributedDataParallel(broadcast_buffers=True)",
+                                            "off": "not broadcast"}[args.ddp_buffers] if world > 1 else None),
                            "empty_cache_every_step": bool(args.empty_cache),
                            "arena_bytes": int(cabi.lib().lg_arena_bytes()),
                            "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",

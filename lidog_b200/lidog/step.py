@@ -58,10 +58,11 @@ class LidogTrainer:
     """Owns model + Adam; `training_step` takes raw device point clouds."""
 
     def __init__(self, model, num_classes=7, voxel_size=0.05, ignore_label=-1, lr=1e-3, weight_decay=1e-4,
-                 source_weights=(0.5, 0.5), shape="kitti", ME=None):
+                 source_weights=(0.5, 0.5), shape="kitti", ME=None, buffer_sync=None):
         if ME is None:
             from lidog_b200 import me as ME
         self.ME, self.model = ME, model
+        self.buffer_sync = buffer_sync  # lidog/ddp.py FlatBuffers: rank 0's BN buffers broadcast at the start of a step
         self.num_classes, self.voxel_size, self.ignore_label = num_classes, voxel_size, ignore_label
         self.source_weights = source_weights
         self.bound, self.bev_img = SHAPES[shape]["bound"], SHAPES[shape]["bev_img"]
@@ -119,6 +120,8 @@ class LidogTrainer:
         return self.source_weights[0] * loss_3d + self.source_weights[1] * loss_bev, loss_3d, loss_bev
 
     def training_step(self, points_list, labels_list):
+        if self.buffer_sync is not None:
+            self.buffer_sync.broadcast()
         with _range("lidog/voxelize"):
             coords, feats, sem_labels, bev_labels, cm = self.voxelize(points_list, labels_list)
         self.optimizer.zero_grad(set_to_none=True)
@@ -136,6 +139,8 @@ class LidogTrainer:
         total = sum_i source_weights[i] * (loss_3d_i + loss_bev_i), one backward, one optimizer step.
         `sources` = [(points_list, labels_list), ...] (two in the reference)."""
         assert len(sources) == len(self.source_weights), "one weight per source domain"
+        if self.buffer_sync is not None:
+            self.buffer_sync.broadcast()
         batches = self.voxelize_multi(sources)
         self.optimizer.zero_grad(set_to_none=True)
         total = None

@@ -88,3 +88,35 @@ def test_sync_batchnorm_conversion_keeps_state():
     assert all(isinstance(x.bn, torch.nn.SyncBatchNorm) for x in s.modules() if isinstance(x, ME.MinkowskiSyncBatchNorm))
     # the dense 2D head keeps plain BatchNorm2d (only MinkowskiBatchNorm is converted)
     assert any(isinstance(x, torch.nn.BatchNorm2d) for x in s.modules())
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lidog_b200.lidog import ddp as lddp
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.BatchNorm1d(8), torch.nn.Linear(8, 6), torch.nn.BatchNorm1d(6))
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    ddp, fb = lddp.wrap(net, buffers="flat")
+    assert fb.intact() and len(fb.flat) == 2  # float32 statistics + int64 num_batches_tracked
+    for k, v in net.state_dict().items():  # re-binding the buffers as views changed no value and no key
+        assert torch.equal(v, before[k]), k
+    ddp.train()
+    torch.manual_seed(10 + rank)  # different data per rank -> un-synchronised BN running statistics diverge
+    ddp(torch.randn(16, 4) * (1 + rank)).sum().backward()
+    local = {k: v.clone() for k, v in net.named_buffers()}
+    fb.broadcast()  # what DDP(broadcast_buffers=True) does at the start of the next forward
+    torch.save({"local": local, "synced": {k: v.clone() for k, v in net.named_buffers()}}, os.path.join(out, f"b{rank}.pt"))
+    assert fb.intact()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_flat_buffer_broadcast_makes_rank0_authoritative(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_flat_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    b0, b1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert any(not torch.equal(b0["local"][k], b1["local"][k]) for k in b0["local"])  # they did diverge
+    for k in b0["local"]:
+        assert torch.equal(b0["synced"][k], b0["local"][k]), k  # rank 0 keeps its own
+        assert torch.equal(b1["synced"][k], b0["local"][k]), k  # rank 1 now holds rank 0's

@@ -70,9 +70,8 @@ for step in "$@"; do
                 bench.py --gpus $NG --steps 8 --warmup 3 $A > ${O}_${step}_${NG}gpu.json 2> ${O}_${step}_${NG}gpu.err
               tail -1 ${O}_${step}_${NG}gpu.err | cut -c1-200; cut -c1-400 ${O}_${step}_${NG}gpu.json ;;
     ddp_ab)   NG=${NG:-$(nvidia-smi -L | wc -l)}   # variants: "ENV=.. ENV=..|bench flags"
-              for V in "|" "|--ddp-broadcast-buffers 0" "|--ddp-broadcast-buffers 0 --ddp-static-graph 1" \
-                       "LIDOG_SM_RESERVE=8|--ddp-broadcast-buffers 0" "LIDOG_SM_RESERVE=16|--ddp-broadcast-buffers 0" \
-                       "|--ddp-broadcast-buffers 0 --no-syncbn" "|"; do
+              for V in "|--ddp-buffers flat" "|--ddp-buffers ddp" "|--ddp-buffers off" "|--ddp-buffers flat --no-syncbn" \
+                       "|--ddp-buffers flat --same-data" "|--ddp-buffers flat"; do
                 E="${V%%|*}"; A="${V#*|}"
                 echo "== env[$E] $A" | tee -a ${O}_ddp_ab_${NG}gpu.txt
                 timeout 600 env $E python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
