@@ -90,4 +90,16 @@ def patch_reference_model(model, policy="last"):
                             policy=policy)
 
     model.sparse2super = types.MethodType(_s2s, model)
+
+    # the dense head's DoubleConv (utils/models/conv2d.py:9-25): BN + ReLU pairs on the fused kernels
+    def _double_conv(self, x):
+        from lidog_b200.me.norm import double_conv_forward
+        return double_conv_forward(self.double_conv, x)
+
+    for m in model.modules():
+        seq = getattr(m, "double_conv", None)
+        if (isinstance(seq, torch.nn.Sequential) and len(seq) == 6 and isinstance(seq[1], torch.nn.BatchNorm2d)
+                and isinstance(seq[2], torch.nn.ReLU) and isinstance(seq[4], torch.nn.BatchNorm2d)
+                and isinstance(seq[5], torch.nn.ReLU)):
+            m.forward = types.MethodType(_double_conv, m)
     return model

@@ -36,7 +36,9 @@ CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1")),
           # 1 = one library call per layer each way (lg_bn_layer_forward / _backward); 0 = fine-grained calls
           "layer_calls": int(os.environ.get("LIDOG_LAYER_CALLS", "1")),
           # 1 = layers without a residual recompute the ReLU mask from x in the backward instead of reading y
-          "recompute_mask": int(os.environ.get("LIDOG_BN_RECOMPUTE_MASK", "1"))}
+          "recompute_mask": int(os.environ.get("LIDOG_BN_RECOMPUTE_MASK", "1")),
+          # 1 = BatchNorm2d + ReLU of the dense BEV head on the fused kernels too (channels_last memory)
+          "head2d": int(os.environ.get("LIDOG_FUSED_HEAD_BN", "1"))}
 C_byref = _C.byref
 
 from ._grad16 import publish_grad16
@@ -113,7 +115,7 @@ class FusedBNFunction(torch.autograd.Function):
         x = x.contiguous()
         n, C = x.shape
         dev = x.device
-        fmt = _fmt16()
+        fmt = None if box.get("no16") else _fmt16()  # no16: no convolution of this library consumes y (dense 2D head)
         y = torch.empty_like(x)
         y16 = torch.empty((n, C), dtype=_dtype16(fmt), device=dev) if fmt is not None else None
         n_st = 4 * C + 4  # [4C + 2] used; rows of the two-branch tensor must stay 16-byte aligned (float4 reads)
@@ -192,6 +194,32 @@ class FusedBNFunction(torch.autograd.Function):
             if use16:
                 publish_grad16(dx2, dx2_16, scales[4:], fmt)
         return dx, dw, db, dx2, dw2, db2, dres, None, None, None
+
+
+def bn_relu_2d(x: torch.Tensor, bn) -> torch.Tensor:
+    """`nn.BatchNorm2d` -> `nn.ReLU` of the dense BEV head (`utils/models/conv2d.py:9-25`, DoubleConv) on the
+    fused kernels: a channels_last [B, C, H, W] tensor IS a row-major [B*H*W, C] matrix.  One statistics pass, the
+    tail kernel and one apply pass with the ReLU inside (12 B/element instead of cuDNN BN + in-place clamp = 20), and a
+    backward that recomputes the mask (20 B/element instead of threshold_backward + cuDNN BN backward ~ 32).  Anything
+    else (eval mode, NCHW memory, CPU) takes the torch modules."""
+    if not (CONFIG["fused"] and CONFIG["head2d"] and bn.training and x.is_cuda and x.dtype == torch.float32
+            and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and bn.affine
+            and (bn.momentum is not None or not bn.track_running_stats)
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return torch.relu_(bn(x))
+    B, C, H, W = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(B * H * W, C)  # a view: channels_last memory is [B, H, W, C] row-major
+    y = FusedBNFunction.apply(rows, bn.weight, bn.bias, None, None, None, None, (bn, None, None, None, None), True,
+                              {"no16": True})
+    return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def double_conv_forward(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Forward of the reference's `DoubleConv.double_conv` = Sequential(Conv2d, BatchNorm2d, ReLU, Conv2d, BatchNorm2d,
+    ReLU) with the two BN + ReLU pairs on the fused kernels (same modules, same parameters, same state-dict keys)."""
+    if x.is_cuda and seq[1].training:
+        return bn_relu_2d(seq[3](bn_relu_2d(seq[0](x), seq[1])), seq[4])
+    return seq(x)
 
 
 class FusedBNFunctionFine(torch.autograd.Function):

@@ -166,3 +166,46 @@ def test_fused_bn_eval_mode_uses_running_statistics(cuda):
     y = bn(ME.SparseTensor(x, coordinate_manager=cm)).F
     ref = torch.nn.functional.batch_norm(x, bn.bn.running_mean, bn.bn.running_var, bn.bn.weight, bn.bn.bias, False)
     assert rel(y, ref) <= 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 37, 41), (3, 256, 20, 23)])
+def test_dense_head_bn_relu_on_the_fused_kernels(cuda, shape):
+    """BatchNorm2d -> ReLU of the dense BEV head (utils/models/conv2d.py:9-25) through bn_relu_2d: a channels_last
+    image is a [B*H*W, C] matrix.  Output, dx, dgamma, dbeta, running statistics vs torch in float64; an NCHW input
+    takes the torch modules (and must give the same numbers)."""
+    from lidog_b200 import cabi
+    from lidog_b200.me import norm
+    from tests.helpers import record
+    torch.manual_seed(5)
+    B, C, H, W = shape
+    x0 = (torch.randn(B, C, H, W, device=cuda) * 2 + 0.3)
+    gy = torch.randn(B, C, H, W, device=cuda)
+    ref_bn = torch.nn.BatchNorm2d(C).to(cuda).double()
+    with torch.no_grad():
+        ref_bn.weight.uniform_(0.5, 1.5)
+        ref_bn.bias.uniform_(-0.5, 0.5)
+    xr = x0.double().requires_grad_(True)
+    yr = torch.relu(ref_bn(xr))
+    yr.backward(gy.double())
+    for fmt_name, mem in (("channels_last", torch.channels_last), ("nchw", torch.contiguous_format)):
+        bn = torch.nn.BatchNorm2d(C).to(cuda)
+        with torch.no_grad():
+            bn.weight.copy_(ref_bn.weight)
+            bn.bias.copy_(ref_bn.bias)
+        x = x0.clone().contiguous(memory_format=mem).requires_grad_(True)
+        cabi.counting(True)  # census mode of the binding: which library entry points ran
+        try:
+            y = norm.bn_relu_2d(x, bn)
+            y.backward(gy.contiguous(memory_format=mem))
+            fused = cabi.COUNTS.get("#lg_bn_layer_forward", 0) > 0 and cabi.COUNTS.get("lg_bn_layer_backward", 0) == 1
+        finally:
+            cabi.counting(False)
+        assert fused == (fmt_name == "channels_last")
+        errs = {"y": rel(y, yr), "dx": rel(x.grad, xr.grad), "dgamma": rel(bn.weight.grad, ref_bn.weight.grad),
+                "dbeta": rel(bn.bias.grad, ref_bn.bias.grad), "running_mean": rel(bn.running_mean, ref_bn.running_mean),
+                "running_var": rel(bn.running_var, ref_bn.running_var)}
+        record({"test": "dense_head_bn_relu", "shape": list(shape), "memory": fmt_name, **errs})
+        bar = 1e-5 if fused else 5e-3  # torch's own float32 BN backward is the loose one (module docstring)
+        assert all(v <= bar for v in errs.values()), (fmt_name, errs)
+        assert int(bn.num_batches_tracked) == 1
+
