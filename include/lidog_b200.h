@@ -305,7 +305,7 @@ typedef struct lgBnBwdBranch {
   const float* x;
   const float* stats; /* [4C + 2] from the forward */
   const float* gamma; /* nullable */
-  float* dx;          /* out [n, C] */
+  float* dx;          /* out [n, C]; nullable when dx16 is given (the consumer reads the 16-bit copy only) */
   void* dx16;         /* nullable out: dx * scale in the 16-bit format, for the convolution backward */
   float *dgamma, *dbeta; /* nullable out [C] (this rank's sums: DDP reduces parameter gradients) */
 } lgBnBwdBranch;

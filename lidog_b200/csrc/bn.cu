@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256)
                    k = *reinterpret_cast<const float4*>(coef + 2 * C + c);
       const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
                                    fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
-      reinterpret_cast<float4*>(dx)[i] = o;
+      if (dx) reinterpret_cast<float4*>(dx)[i] = o;  // NULL: only the 16-bit copy is consumed (a tensor-core convolution)
       if (dx16) store16x4(dx16 + i * 4, make_float4(o.x * s1, o.y * s1, o.z * s1, o.w * s1), fmt);
     }
     if (x2) {
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256)
                    k = *reinterpret_cast<const float4*>(coef2 + 2 * C + c);
       const float4 o = make_float4(fmaf(a.x, g.x, fmaf(b.x, v.x - mu.x, k.x)), fmaf(a.y, g.y, fmaf(b.y, v.y - mu.y, k.y)),
                                    fmaf(a.z, g.z, fmaf(b.z, v.z - mu.z, k.z)), fmaf(a.w, g.w, fmaf(b.w, v.w - mu.w, k.w)));
-      reinterpret_cast<float4*>(dx2)[i] = o;
+      if (dx2) reinterpret_cast<float4*>(dx2)[i] = o;
       if (dx2_16) store16x4(dx2_16 + i * 4, make_float4(o.x * s2, o.y * s2, o.z * s2, o.w * s2), fmt);
     }
     if (dres) {
@@ -859,7 +859,7 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   int rc = bn_check(n > 0 ? n : 1, C, "lg_bn_layer_backward");
   if (rc) return rc;
   LG_CHECK_ARG(n >= 0 && a && a->stats && scales && (!b || b->stats) &&
-                   (n == 0 || (dy && a->x && a->dx && (!b || (b->x && b->dx)))),
+                   (n == 0 || (dy && a->x && (a->dx || a->dx16) && (!b || (b->x && (b->dx || b->dx16))))),
                "lg_bn_layer_backward: null pointer");
   LG_CHECK_ARG(!(relu && dres && !y), "lg_bn_layer_backward: a layer with a residual needs y for its ReLU mask");
   LG_CHECK_ARG(dy_ld >= C && dy_ld % 4 == 0 && ((uintptr_t)dy & 15) == 0,

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import cabi
-from ._grad16 import take_grad16
+from ._grad16 import take_grad16, require_fp32
 from .sparse_tensor import SparseTensor
 
 # operand format of the tensor-core path: "fp16" (default; 2^-11 unit round-off meets the 1e-3 bar),
@@ -183,6 +183,7 @@ class SparseConvFunction(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
+            require_fp32(dy, "convolution bias gradient")
             db = dy.sum(0, keepdim=True)
         if ctx.tc:
             x16, _ = ctx.saved_tensors
@@ -192,6 +193,7 @@ class SparseConvFunction(torch.autograd.Function):
             if hit is not None:
                 dy16, scale = hit
             else:
+                require_fp32(dy, "convolution backward (16-bit copy not usable)")
                 scale = None
                 if fmt == cabi.FMT_FP16:  # bring the gradient into fp16's normal range (power-of-two scale)
                     scale = torch.empty(4, dtype=torch.float32, device=dy.device)
@@ -227,6 +229,7 @@ class SparseConvFunction(torch.autograd.Function):
                     else:
                         launch()
         else:
+            require_fp32(dy, "fp32 convolution backward")
             x, W3c = ctx.saved_tensors
             if ctx.needs_input_grad[0]:
                 dx = _gemm_simt(p_dgrad, dy, W3c, cin, 1, flip, None)

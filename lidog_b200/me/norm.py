@@ -38,7 +38,10 @@ CONFIG = {"fused": int(os.environ.get("LIDOG_FUSED_BN", "1")),
           # 1 = layers without a residual recompute the ReLU mask from x in the backward instead of reading y
           "recompute_mask": int(os.environ.get("LIDOG_BN_RECOMPUTE_MASK", "1")),
           # 1 = BatchNorm2d + ReLU of the dense BEV head on the fused kernels too (channels_last memory)
-          "head2d": int(os.environ.get("LIDOG_FUSED_HEAD_BN", "1"))}
+          "head2d": int(os.environ.get("LIDOG_FUSED_HEAD_BN", "1")),
+          # 1 = where the BN input came straight out of a tensor-core convolution, the backward writes dx in 16 bits
+          # only (that convolution's backward reads nothing else); see me/_grad16.py for the guards
+          "skip_dx32": int(os.environ.get("LIDOG_BN_SKIP_DX32", "1"))}
 C_byref = _C.byref
 
 from ._grad16 import publish_grad16
@@ -152,6 +155,11 @@ class FusedBNFunction(torch.autograd.Function):
         keep_y = relu and (res is not None or x2 is not None or not CONFIG["recompute_mask"])
         ctx.save_for_backward(x, x2, y if keep_y else None, st_a, st_b, w, w2)
         ctx.meta = (relu, res is not None, fmt, ex)
+        # fp32 dx / dx2 are skipped where the input is the output of a tensor-core convolution (it carried epilogue
+        # statistics) and a 16-bit copy is published for that convolution's backward
+        skip = bool(CONFIG["skip_dx32"]) and fmt is not None
+        ctx.skip32 = (skip and sp_a is not None, skip and sp_b is not None)
+        ctx.box = box
         return y
 
     @staticmethod
@@ -168,17 +176,21 @@ class FusedBNFunction(torch.autograd.Function):
         d16 = _dtype16(fmt) if use16 else None
         scales = torch.empty(12, dtype=torch.float32, device=dev)
 
-        def branch(xt, st, gamma):
-            dx = torch.empty_like(xt)
+        def branch(xt, st, gamma, skip32):
+            dx = torch.empty_like(xt)  # autograd's handle; its values are written unless skip32
             dx16 = torch.empty((n, C), dtype=d16, device=dev) if use16 else None
             dgb = torch.empty((2, C), dtype=torch.float32, device=dev)
-            return dx, dx16, dgb, cabi.BnBwdBranch(xt.data_ptr(), st.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
+            return dx, dx16, dgb, cabi.BnBwdBranch(xt.data_ptr(), st.data_ptr(), gamma.data_ptr(),
+                                                   None if skip32 else dx.data_ptr(),
                                                    cabi.ptr(dx16), dgb.data_ptr(), dgb.data_ptr() + 4 * C)
 
-        dx, dx16, dgb, br_a = branch(x, st_a, w)
+        skip_a, skip_b = ctx.skip32[0] and use16, ctx.skip32[1] and use16
+        dx, dx16, dgb, br_a = branch(x, st_a, w, skip_a)
+        ctx.box["dx_ptr"] = dx.data_ptr() if skip_a else None  # read by _sole_consumer_guard
         dx2 = dx2_16 = dgb2 = br_b = None
         if x2 is not None:
-            dx2, dx2_16, dgb2, br_b = branch(x2, st_b, w2)
+            dx2, dx2_16, dgb2, br_b = branch(x2, st_b, w2, skip_b)
+            ctx.box["dx2_ptr"] = dx2.data_ptr() if skip_b else None
             br_b = C_byref(br_b)
         dres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[6]) else None
         cabi.check(L.lg_bn_layer_backward(dy.data_ptr(), dy.stride(0) if n > 1 else C, cabi.ptr(y), 1 if relu else 0, n, C,
@@ -366,6 +378,11 @@ class DeferredBN(SparseTensor):
         if CONFIG["layer_calls"] and (pg is None or ex is not None):
             sp_a = _partials_of(src)
             sp_b = _partials_of(r._src) if x2 is not None else None
+            if CONFIG["skip_dx32"] and torch.is_grad_enabled():
+                if sp_a is not None:
+                    _sole_consumer_guard(src.F, box, "dx_ptr")
+                if sp_b is not None:
+                    _sole_consumer_guard(x2, box, "dx2_ptr")
             self._value = FusedBNFunction.apply(src.F, bn.weight, bn.bias, x2, w2, b2, res, (bn, bn_b, sp_a, sp_b, ex),
                                                 bool(relu), box)
         else:

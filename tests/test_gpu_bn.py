@@ -209,3 +209,34 @@ def test_dense_head_bn_relu_on_the_fused_kernels(cuda, shape):
         assert all(v <= bar for v in errs.values()), (fmt_name, errs)
         assert int(bn.num_batches_tracked) == 1
 
+
+def test_skipped_fp32_gradient_is_guarded(cuda):
+    """conv -> BN -> ReLU: the BN backward hands the convolution a 16-bit gradient only (LIDOG_BN_SKIP_DX32=1).  Same
+    results as with the fp32 gradient written; a second consumer of the convolution output must fail loudly."""
+    ME, cm, n = _sparse(cuda, 5000)
+    from lidog_b200.me import norm, _grad16
+    torch.manual_seed(2)
+    conv = ME.MinkowskiConvolution(32, 64, kernel_size=3, dimension=3).to(cuda)
+    x0 = torch.randn(n, 32, device=cuda).relu_()
+    gy = torch.randn(n, 64, device=cuda) * 1e-3
+    outs = []
+    for skip in (1, 0):
+        norm.CONFIG["skip_dx32"] = skip
+        try:
+            bn = ME.MinkowskiBatchNorm(64).to(cuda)
+            x = x0.clone().requires_grad_(True)
+            conv.kernel.grad = None
+            y = ME.MinkowskiReLU()(bn(conv(ME.SparseTensor(x, coordinate_manager=cm)))).F
+            y.backward(gy)
+            outs.append((y.detach(), x.grad.clone(), conv.kernel.grad.clone(), bn.bn.weight.grad.clone()))
+            assert len(_grad16._TABLE) == 0 and len(_grad16._NO_FP32) == 0
+        finally:
+            norm.CONFIG["skip_dx32"] = 1
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)  # the 16-bit copy is what the convolution reads either way
+    bn = ME.MinkowskiBatchNorm(64).to(cuda)
+    mid = conv(ME.SparseTensor(x0.clone().requires_grad_(True), coordinate_manager=cm))
+    y = ME.MinkowskiReLU()(bn(mid)).F + mid.F  # second consumer of the convolution output
+    with pytest.raises(RuntimeError, match="LIDOG_BN_SKIP_DX32"):
+        y.backward(gy)
+    _grad16.clear()
