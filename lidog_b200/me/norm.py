@@ -200,12 +200,29 @@ class FusedBNFunction(torch.autograd.Function):
         dw, db = dgb[0], dgb[1]
         dw2 = db2 = None
         if use16:
-            publish_grad16(dx, dx16, scales, fmt)
+            publish_grad16(dx, dx16, scales, fmt, fp32_valid=not skip_a)
         if x2 is not None:
             dw2, db2 = dgb2[0], dgb2[1]
             if use16:
-                publish_grad16(dx2, dx2_16, scales[4:], fmt)
+                publish_grad16(dx2, dx2_16, scales[4:], fmt, fp32_valid=not skip_b)
         return dx, dw, db, dx2, dw2, db2, dres, None, None, None
+
+
+def _sole_consumer_guard(t: torch.Tensor, box: dict, key: str) -> None:
+    """The BN backward may leave the fp32 gradient of `t` unwritten (skip_dx32): make sure the gradient autograd
+    hands to t's producer IS the tensor this layer returned -- a second consumer of t would make autograd sum ours
+    (uninitialised) with theirs."""
+    if not t.requires_grad:
+        return
+
+    def check(grad):
+        want = box.get(key)  # None: the fp32 gradient was written after all
+        if want is not None and grad.data_ptr() != want:
+            raise RuntimeError("a convolution output that feeds a fused batch norm has a second consumer; its fp32 "
+                               "gradient is needed: set LIDOG_BN_SKIP_DX32=0")
+        return None
+
+    t.register_hook(check)
 
 
 def bn_relu_2d(x: torch.Tensor, bn) -> torch.Tensor:
