@@ -16,6 +16,8 @@ for step in "$@"; do
     tests_e2e) timeout 900 python -m pytest tests/test_gpu_fullscale.py tests/test_gpu_model.py tests/test_gpu_trainer.py -m gpu -q 2>&1 | tail -15 | tee ${O}_gpu_tests_e2e.log ;;
     smoke)    timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee ${O}_smoke.log ;;
     bench)    timeout 900 python bench.py --steps 8 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
+    bench_ref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_reference.json 2> ${O}_bench_reference.err; cat ${O}_bench_reference.json | cut -c1-600 ;;
+    bench_default) ( time timeout 900 python bench.py ) > ${O}_bench_default.json 2> ${O}_bench_default.err; tail -5 ${O}_bench_default.err | cut -c1-300 ;;
     bench_nocpu) timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > ${O}_bench.json 2> ${O}_bench.err; tail -2 ${O}_bench.err | cut -c1-400 ;;
     bench_ab) for cfg in "LIDOG_LAYER_CALLS=0" "LIDOG_EPI_STATS=0"; do
                 env $cfg timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > ${O}_bench_${cfg}.json 2> ${O}_bench_${cfg}.err
