@@ -159,7 +159,6 @@ class FusedBNFunction(torch.autograd.Function):
         # statistics) and a 16-bit copy is published for that convolution's backward
         skip = bool(CONFIG["skip_dx32"]) and fmt is not None
         ctx.skip32 = (skip and sp_a is not None, skip and sp_b is not None)
-        ctx.box = box
         return y
 
     @staticmethod
@@ -186,11 +185,9 @@ class FusedBNFunction(torch.autograd.Function):
 
         skip_a, skip_b = ctx.skip32[0] and use16, ctx.skip32[1] and use16
         dx, dx16, dgb, br_a = branch(x, st_a, w, skip_a)
-        ctx.box["dx_ptr"] = dx.data_ptr() if skip_a else None  # read by _sole_consumer_guard
         dx2 = dx2_16 = dgb2 = br_b = None
         if x2 is not None:
             dx2, dx2_16, dgb2, br_b = branch(x2, st_b, w2, skip_b)
-            ctx.box["dx2_ptr"] = dx2.data_ptr() if skip_b else None
             br_b = C_byref(br_b)
         dres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[6]) else None
         cabi.check(L.lg_bn_layer_backward(dy.data_ptr(), dy.stride(0) if n > 1 else C, cabi.ptr(y), 1 if relu else 0, n, C,
@@ -206,23 +203,6 @@ class FusedBNFunction(torch.autograd.Function):
             if use16:
                 publish_grad16(dx2, dx2_16, scales[4:], fmt, fp32_valid=not skip_b)
         return dx, dw, db, dx2, dw2, db2, dres, None, None, None
-
-
-def _sole_consumer_guard(t: torch.Tensor, box: dict, key: str) -> None:
-    """The BN backward may leave the fp32 gradient of `t` unwritten (skip_dx32): make sure the gradient autograd
-    hands to t's producer IS the tensor this layer returned -- a second consumer of t would make autograd sum ours
-    (uninitialised) with theirs."""
-    if not t.requires_grad:
-        return
-
-    def check(grad):
-        want = box.get(key)  # None: the fp32 gradient was written after all
-        if want is not None and grad.data_ptr() != want:
-            raise RuntimeError("a convolution output that feeds a fused batch norm has a second consumer; its fp32 "
-                               "gradient is needed: set LIDOG_BN_SKIP_DX32=0")
-        return None
-
-    t.register_hook(check)
 
 
 def bn_relu_2d(x: torch.Tensor, bn) -> torch.Tensor:
@@ -395,11 +375,6 @@ class DeferredBN(SparseTensor):
         if CONFIG["layer_calls"] and (pg is None or ex is not None):
             sp_a = _partials_of(src)
             sp_b = _partials_of(r._src) if x2 is not None else None
-            if CONFIG["skip_dx32"] and torch.is_grad_enabled():
-                if sp_a is not None:
-                    _sole_consumer_guard(src.F, box, "dx_ptr")
-                if sp_b is not None:
-                    _sole_consumer_guard(x2, box, "dx2_ptr")
             self._value = FusedBNFunction.apply(src.F, bn.weight, bn.bias, x2, w2, b2, res, (bn, bn_b, sp_a, sp_b, ex),
                                                 bool(relu), box)
         else:
