@@ -20,7 +20,7 @@ _NO_FP32 = set()  # data pointers of published gradients whose fp32 tensor was n
 
 
 def publish_grad16(grad: torch.Tensor, grad16: torch.Tensor, scale: torch.Tensor, fmt: int, fp32_valid: bool = True) -> None:
-    _TABLE[grad.data_ptr()] = (grad, grad16, scale, fmt)
+    _TABLE[grad.data_ptr()] = (grad, grad16, scale, fmt, grad._version)  # version at publication time
     if not fp32_valid:
         _NO_FP32.add(grad.data_ptr())
 
@@ -30,8 +30,8 @@ def take_grad16(grad: torch.Tensor, fmt: int):
     hit = _TABLE.get(grad.data_ptr())
     if hit is None:
         return None
-    g, g16, scale, f = hit
-    if g.shape != grad.shape or g._version != grad._version or g.stride() != grad.stride() or f != fmt:
+    g, g16, scale, f, version = hit
+    if g.shape != grad.shape or version != grad._version or g.stride() != grad.stride() or f != fmt:
         if grad.data_ptr() not in _NO_FP32:
             del _TABLE[grad.data_ptr()]  # fp32 values exist: the caller casts them itself
         return None
