@@ -341,17 +341,20 @@ def run_ours(args):
     launches = cabi.kernel_launches()
     cabi.counting(False)
     recs, inst_ms, k_steps = [], 1.0, 1
-    if world == 1:  # the kernel roofline is a single-GPU statement; multi-GPU runs only report throughput
-        meconv.PROFILE.update(enabled=True, events=False)
-        meconv.PROFILE["records"].clear()
-        resident_step()
-        torch.cuda.synchronize()
-        k_steps = min(args.steps, 4)
-        meconv.PROFILE.update(enabled=True, events=True)
-        meconv.PROFILE["records"].clear()
-        inst_ms = timed(resident_step, k_steps)
-        recs = list(meconv.PROFILE["records"])
-        meconv.PROFILE.update(enabled=False, events=False)
+    # Instrumented pass: every rank runs the same steps (the SyncBN exchanges and the DDP all-reduce need all of them),
+    # rank 0 alone wraps its convolution launches in CUDA events -- at N > 1 the roofline is rank 0's kernels inside
+    # a data-parallel step, NCCL traffic included.
+    prof = rank == 0
+    meconv.PROFILE.update(enabled=prof, events=False)
+    meconv.PROFILE["records"].clear()
+    resident_step()
+    torch.cuda.synchronize()
+    k_steps = min(args.steps, 4)
+    meconv.PROFILE.update(enabled=prof, events=prof)
+    meconv.PROFILE["records"].clear()
+    inst_ms = timed(resident_step, k_steps)
+    recs = list(meconv.PROFILE["records"])
+    meconv.PROFILE.update(enabled=False, events=False)
 
     # roofline of the dominant kernel (tcgen05 gather-GEMM: fwd + dgrad launches), from the instrumented pass
     pk = peaks()
