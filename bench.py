@@ -12,6 +12,7 @@ configs[1] (batch 8 scans per GPU, 7 classes, DDP + SyncBN when N > 1).  One JSO
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -290,14 +291,22 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         mecoords.SYNC_WAIT.update(seconds=0.0, count=0)
-        t0 = time.perf_counter()
+        marks = []
+        gc.collect()
+        gc.disable()  # a generation-2 collection inside the loop stalls one rank for tens of ms -- and, through the
+        t0 = time.perf_counter()  # SyncBN exchanges, every other rank with it
         e0.record()
         for _ in range(steps):
             fn()
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
         e1.record()
+        gc.enable()
         host["issue_ms"] = 1e3 * (time.perf_counter() - t0) / steps  # wall time of the host loop, waits included
         host["wait_ms"] = 1e3 * mecoords.SYNC_WAIT["seconds"] / steps  # of which: blocked in the step's one sync
         barrier()
+        host["step_ms"] = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)]  # this rank's steps
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -431,6 +440,7 @@ def run_ours(args):
                            "bev_layout": "channels_last" if lbev.CONFIG["channels_last"] else "nchw"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "sparse_conv_ms_per_scan": conv_ms / args.batch, "kernels": kernels,
+                "rank0_step_ms": step_ms,  # per step of the headline loop, CUDA events on rank 0 (diagnostic)
                 "host_issue_ms_per_step": host_issue_ms, "host_wait_ms_per_step": host_wait_ms,
                 "host_busy_ms_per_step": None if host_issue_ms is None else host_issue_ms - host_wait_ms,
                 "host_note": "issue = wall time of the Python loop for one step; wait = the part spent blocked in the "
