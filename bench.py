@@ -339,6 +339,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms = timed(resident_step, args.steps)
     host_issue_ms, host_wait_ms = host.get("issue_ms"), host.get("wait_ms")
+    step_ms = host.get("step_ms")
     clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * args.batch / (ms_per_step / 1e3)
