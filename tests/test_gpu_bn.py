@@ -204,7 +204,7 @@ def test_dense_head_bn_relu_on_the_fused_kernels(cuda, shape):
         errs = {"y": rel(y, yr), "dx": rel(x.grad, xr.grad), "dgamma": rel(bn.weight.grad, ref_bn.weight.grad),
                 "dbeta": rel(bn.bias.grad, ref_bn.bias.grad), "running_mean": rel(bn.running_mean, ref_bn.running_mean),
                 "running_var": rel(bn.running_var, ref_bn.running_var)}
-        record({"test": "dense_head_bn_relu", "shape": list(shape), "memory": fmt_name, **errs})
+        record("dense_head_bn_relu", shape=list(shape), memory=fmt_name, **errs)
         bar = 1e-5 if fused else 5e-3  # torch's own float32 BN backward is the loose one (module docstring)
         assert all(v <= bar for v in errs.values()), (fmt_name, errs)
         assert int(bn.num_batches_tracked) == 1
