@@ -439,7 +439,10 @@ def run_ours(args):
                            "layer_calls": bool(meconv.CONFIG["layer_calls"]), "epilogue_bn_stats": bool(meconv.CONFIG["epi_stats"]),
                            "fused_bn": bool(menorm.CONFIG["fused"]),
                            "bev_layout": "channels_last" if lbev.CONFIG["channels_last"] else "nchw"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                # own kernels (liblidog_b200.so) launched inside the timed region: a census step counts them per step
+                # (the census is a separate, untimed step: the headline loop carries no counting), per rank
+                "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+                "clocks": clocks, "roofline": roofline,
                 "sparse_conv_ms_per_scan": conv_ms / args.batch, "kernels": kernels,
                 "rank0_step_ms": step_ms,  # per step of the headline loop, CUDA events on rank 0 (diagnostic)
                 "host_issue_ms_per_step": host_issue_ms, "host_wait_ms_per_step": host_wait_ms,
