@@ -311,8 +311,9 @@ typedef struct lgBnBwdBranch {
 } lgBnBwdBranch;
 /* Backward of the above.  scales float[12]: [4i .. 4i+2] = {2^k, 2^-k, bound} of branch i's dx16. dres (nullable)
  * receives g = dy * [y > 0], the gradient of the plain residual.  y (the forward output) is only read for the ReLU
- * mask; y == NULL with relu says "the forward had no residual": the mask is then recomputed from x (and x2) with the
- * forward's own expression (bit-identical), and the two passes read 8 bytes per element less. */
+ * mask; y == NULL with relu says "the forward had neither a residual nor a second branch": the mask is then
+ * recomputed from x with the forward's own expression (bit-identical) and the two passes read 8 bytes per element
+ * less; with a residual or a second branch y is required (LG_ERR_INVALID otherwise). */
 int lg_bn_layer_backward(const float* dy, int64_t dy_ld /* row pitch of dy in floats (>= C): the gradient of one input
                          of ME.cat is a column slice of a wider matrix and is consumed in place */,
                          const float* y, int32_t relu, int64_t n, int32_t C, const lgBnBwdBranch* a,

@@ -873,7 +873,8 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
   LG_CHECK_ARG(n >= 0 && a && a->stats && scales && (!b || b->stats) &&
                    (n == 0 || (dy && a->x && (a->dx || a->dx16) && (!b || (b->x && (b->dx || b->dx16))))),
                "lg_bn_layer_backward: null pointer");
-  LG_CHECK_ARG(!(relu && dres && !y), "lg_bn_layer_backward: a layer with a residual needs y for its ReLU mask");
+  LG_CHECK_ARG(!(relu && !y && (dres || b)),
+               "lg_bn_layer_backward: a layer with a residual or a second branch needs y for its ReLU mask");
   LG_CHECK_ARG(dy_ld >= C && dy_ld % 4 == 0 && ((uintptr_t)dy & 15) == 0,
                "lg_bn_layer_backward: dy needs a row pitch >= C that is a multiple of 4 floats and 16-byte alignment");
   int sm = 0;
@@ -900,11 +901,10 @@ extern "C" int lg_bn_layer_backward(const float* dy, int64_t dy_ld, const float*
     case 0: LG_BWD_STATS(false, false, false); break;
     case 1: LG_BWD_STATS(false, false, true); break;
     case 2: LG_BWD_STATS(false, true, false); break;
-    case 3: LG_BWD_STATS(false, true, true); break;
     case 4: LG_BWD_STATS(true, false, false); break;
     case 5: LG_BWD_STATS(true, false, true); break;
     case 6: LG_BWD_STATS(true, true, false); break;
-    default: LG_BWD_STATS(true, true, true); break;
+    default: break;  // recomputation with two branches is refused above
   }
 #undef LG_BWD_STATS
   LG_LAUNCH_OK();
